@@ -1,0 +1,226 @@
+"""ddc_svd_b200 — host-side Python mirror of the reference's C interface for the svd_gpu() path.
+
+The product is ``libsvdgpu.so`` (C ABI, built by ``make`` / ``__graft_entry__.build()`` from
+``csrc/*.cu`` + ``host/*.c`` for sm_100a).  This module only binds it with ctypes, with the
+reference's names, argument meaning and layouts (column-major, ascending sigma):
+
+    svd_gpu(m, n, A, sigma, U, V)                       svd_gpu.h:5
+    bidiag_par(m, n, A, alpha, beta)                    bidiag_par.h:30
+    GetSingularValues_Parallel(N, b1, b2, sigma)        Calculations-Parallel.h:41
+    CalcRightSingularVectors / RighttoLeftSingularVectors   parallel-twisted.h:18-19
+    multU / multV                                       bidiag_par.h:72-73
+
+There is no CPU fallback: importing works anywhere, but every compute call needs the
+library and a CUDA device and fails loudly otherwise.  Nothing here touches ``oracle/``.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsvdgpu.so")
+_lib = None
+
+c_double_p = ctypes.POINTER(ctypes.c_double)
+c_float_p = ctypes.POINTER(ctypes.c_float)
+c_void_p = ctypes.c_void_p
+c_int, c_long, c_size_t, c_double = ctypes.c_int, ctypes.c_long, ctypes.c_size_t, ctypes.c_double
+
+# (name, restype, argtypes) for every symbol include/*.h declares
+SIGNATURES = [
+    # include/svd_gpu.h
+    ("svd_gpu", None, [c_int, c_int, c_double_p, c_double_p, c_double_p, c_double_p]),
+    # include/svd_gpu_b200.h
+    ("svd_gpu_dev", None, [c_int, c_int, c_void_p, c_long, c_void_p, c_void_p, c_long, c_void_p, c_long, c_void_p]),
+    ("svd_gpu_vectors_dev", None, [c_int, c_int, c_void_p, c_long, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                   c_void_p, c_long, c_void_p, c_long, c_void_p, c_void_p]),
+    ("svd_gpu_values_dev", None, [c_int, c_int, c_void_p, c_long, c_void_p, c_void_p, c_void_p, c_void_p]),
+    ("svd_gpu_last_phase_ms", None, [c_float_p]),
+    ("svd_gpu_set_option", None, [ctypes.c_char_p, c_int]),
+    # include/bidiag_par.h
+    ("bidiag_par", None, [c_int, c_int, c_double_p, c_double_p, c_double_p]),
+    ("multU", None, [c_int, c_int, c_int, c_double_p, c_double_p, c_double_p]),
+    ("multV", None, [c_int, c_int, c_int, c_double_p, c_double_p, c_double_p]),
+    ("svd_gpu_backtransform", None, [c_int, c_int, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
+    # include/Calculations-Parallel.h
+    ("GetSingularValues_Parallel", None, [c_int, c_double_p, c_double_p, c_double_p]),
+    # include/parallel-twisted.h
+    ("CalcRightSingularVectors", None, [c_int, c_int, c_double_p, c_double_p, c_double_p, c_double_p]),
+    ("RighttoLeftSingularVectors", None, [c_int, c_int, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
+    # include/matrix_helper.h
+    ("transpose", None, [c_int, c_int, c_double_p, c_double_p]),
+    ("form_bidiag", None, [c_int, c_int, c_double_p, c_double_p, c_double_p]),
+    ("dgemm_simple", None, [c_int, c_int, c_int, c_double_p, c_double_p, c_double_p]),
+    ("l2_norm_mat", c_double, [c_int, c_int, c_double_p]),
+    ("l2_normv", c_double, [c_int, c_double_p]),
+    ("dot_prod", c_double, [c_int, c_double_p, c_double_p]),
+    ("scale_vector", None, [c_int, c_double_p, c_double]),
+    ("l2_norm_mat_row", c_double, [c_int, c_int, c_int, c_double_p]),
+    ("scale_mat_row", None, [c_int, c_int, c_int, c_double_p, c_double]),
+    ("dot_prod_mat_rows", c_double, [c_int, c_int, c_int, c_double_p, c_double_p]),
+    ("dot_prod_mat_row_with_vec", c_double, [c_int, c_int, c_int, c_double_p, c_double_p]),
+    ("set_vec_to_zero", None, [c_int, c_double_p]),
+    ("print_matrix", None, [c_double_p, c_long, c_long, ctypes.c_char_p]),
+    # include/cuda-helper.h
+    ("svdgpu_device_count", c_int, []),
+    ("svdgpu_set_device", None, [c_int]),
+    ("svdgpu_get_device", c_int, []),
+    ("svdgpu_device_name", ctypes.c_char_p, []),
+    ("svdgpu_malloc", c_void_p, [c_size_t]),
+    ("svdgpu_free", None, [c_void_p]),
+    ("svdgpu_memset", None, [c_void_p, c_int, c_size_t, c_void_p]),
+    ("svdgpu_h2d", None, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    ("svdgpu_d2h", None, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    ("svdgpu_d2d", None, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    ("svdgpu_h2d_2d", None, [c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_size_t, c_void_p]),
+    ("svdgpu_d2h_2d", None, [c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_size_t, c_void_p]),
+    ("svdgpu_stream_create", c_void_p, []),
+    ("svdgpu_stream_destroy", None, [c_void_p]),
+    ("svdgpu_stream_sync", None, [c_void_p]),
+    ("svdgpu_stream_wait_event", None, [c_void_p, c_void_p]),
+    ("svdgpu_event_create", c_void_p, []),
+    ("svdgpu_event_destroy", None, [c_void_p]),
+    ("svdgpu_event_record", None, [c_void_p, c_void_p]),
+    ("svdgpu_event_elapsed_ms", ctypes.c_float, [c_void_p, c_void_p]),
+    ("svdgpu_host_alloc", c_void_p, [c_size_t]),
+    ("svdgpu_host_free", None, [c_void_p]),
+    ("svdgpu_bidiag_workspace", c_size_t, [c_int, c_int, c_long]),
+    ("svdgpu_bidiag", None, [c_int, c_int, c_void_p, c_long, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    ("svdgpu_ddc_workspace", c_size_t, [c_int]),
+    ("svdgpu_ddc_values", None, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    ("svdgpu_twisted_workspace", c_size_t, [c_int, c_int, c_int]),
+    ("svdgpu_twisted_vectors", None, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
+                                      c_long, c_void_p, c_long, c_void_p, c_int, c_void_p, c_void_p]),
+    ("svdgpu_backtransform_workspace", c_size_t, [c_int, c_int, c_int]),
+    ("svdgpu_wy_apply", None, [c_int, c_int, c_int, c_void_p, c_long, c_void_p, c_long, c_int, c_void_p, c_void_p]),
+    ("svdgpu_dgemm", None, [c_int, c_int, c_int, c_int, c_int, c_double, c_void_p, c_long, c_void_p, c_long,
+                            c_double, c_void_p, c_long, c_void_p]),
+    ("svdgpu_bidiag_pass_probe", None, [c_int, c_int, c_void_p, c_long, c_void_p, c_int, c_void_p]),
+]
+
+
+def lib():
+    """The loaded C-ABI library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `make` (or __graft_entry__.build()). "
+                "ddc_svd_b200 has no CPU or PyTorch fallback.")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, res, args in SIGNATURES:
+            fn = getattr(L, name)            # AttributeError = a declared symbol is not exported
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(c_double_p)
+
+
+def _colmajor(a):
+    a = np.asarray(a, dtype=np.float64)
+    if a.ndim != 2:
+        raise ValueError("expected a 2-D matrix")
+    return np.array(a, dtype=np.float64, order="F", copy=True)
+
+
+# ----------------------------------------------------------------- reference-shaped host API
+def svd_gpu(A, vectors=True):
+    """svd_gpu(m,n,A,sigma,U,V) on a 2-D array.  Returns (sigma ascending, U m x mn, V n x mn,
+    A_mod) — A_mod is the overwritten A (the Householder reflectors), as the reference leaves it."""
+    Af = _colmajor(A)
+    m, n = Af.shape
+    mn = min(m, n)
+    sigma = np.zeros(mn)
+    if vectors:
+        U = np.zeros((m, mn), order="F")
+        V = np.zeros((n, mn), order="F")
+        lib().svd_gpu(m, n, _p(Af), _p(sigma), _p(U), _p(V))
+        return sigma, U, V, Af
+    lib().svd_gpu(m, n, _p(Af), _p(sigma), None, None)
+    return sigma, None, None, Af
+
+
+def bidiag_par(A):
+    """bidiag_par(m,n,A,alpha,beta): returns (A_mod, alpha[min(m,n)], beta[n-1 | m])."""
+    Af = _colmajor(A)
+    m, n = Af.shape
+    mn = min(m, n)
+    alpha = np.zeros(mn)
+    beta = np.zeros(max(n - 1 if m >= n else m, 1))
+    lib().bidiag_par(m, n, _p(Af), _p(alpha), _p(beta))
+    return Af, alpha, beta[: (n - 1 if m >= n else m)]
+
+
+def get_singular_values(b1, b2):
+    """GetSingularValues_Parallel(N,b1,b2,sigma); b2 is zero-padded to N entries."""
+    b1 = np.ascontiguousarray(b1, dtype=np.float64)
+    N = b1.shape[0]
+    b2p = np.zeros(N)
+    b2p[: len(b2)] = b2
+    sigma = np.zeros(N)
+    lib().GetSingularValues_Parallel(N, _p(b1), _p(b2p), _p(sigma))
+    return sigma
+
+
+def singular_vectors(a, b, sigma, m=None):
+    """CalcRightSingularVectors + RighttoLeftSingularVectors.  Returns X (n x m, row i = x_i, the
+    reference's X[i*m+j]) and Y (n x n, row i = y_i)."""
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    n = a.shape[0]
+    m = n if m is None else m
+    bp = np.zeros(max(m - 1, 1))
+    bp[: min(len(b), m - 1)] = np.asarray(b, dtype=np.float64)[: m - 1]
+    sigma = np.ascontiguousarray(sigma, dtype=np.float64)
+    X = np.zeros((n, m))
+    Y = np.zeros((n, n))
+    lib().RighttoLeftSingularVectors(n, m, _p(a), _p(bp), _p(sigma), _p(X), _p(Y))
+    return X, Y
+
+
+def backtransform(A_mod, X, Y):
+    """All of multU/multV at once: U = Q_L [Y^T;0], V = Q_R [X^T;0] (X, Y as returned above)."""
+    Af = _colmajor(A_mod)
+    m, n = Af.shape
+    mn = min(m, n)
+    U = np.zeros((m, mn), order="F")
+    V = np.zeros((n, mn), order="F")
+    Xc = np.ascontiguousarray(X, dtype=np.float64)
+    Yc = np.ascontiguousarray(Y, dtype=np.float64)
+    lib().svd_gpu_backtransform(m, n, _p(Af), _p(Xc), _p(Yc), _p(U), _p(V))
+    return U, V
+
+
+def last_phase_ms():
+    """[h2d, bidiag, dDC, twisted, back-transform, d2h, total] of the last svd_gpu/svd_gpu_dev call."""
+    ms = (ctypes.c_float * 7)()
+    lib().svd_gpu_last_phase_ms(ms)
+    return list(ms)
+
+
+def set_option(name, value):
+    lib().svd_gpu_set_option(name.encode(), int(value))
+
+
+# ----------------------------------------------------------------- device-resident API (torch)
+def svd_gpu_dev(tA, tsigma, tU=None, tV=None, stream=None):
+    """svd_gpu_dev on torch CUDA tensors.  tA holds the m x n matrix COLUMN-MAJOR, i.e. it is a
+    contiguous (n, lda) float64 tensor whose row j is column j of A (lda even >= m); tU (mn, m) and
+    tV (mn, n) likewise hold U and V column by column.  Enqueues on `stream` (default: torch's
+    current stream) so torch.cuda.Event timing brackets it."""
+    import torch
+    n, lda = tA.shape
+    mn = tsigma.shape[0]
+    m = tU.shape[1] if tU is not None else None
+    if m is None:
+        raise ValueError("pass m via svd_gpu_dev_raw for values-only runs")
+    st = torch.cuda.current_stream().cuda_stream if stream is None else stream
+    lib().svd_gpu_dev(m, n, tA.data_ptr(), lda, tsigma.data_ptr(), tU.data_ptr(), tU.shape[1],
+                      tV.data_ptr(), tV.shape[1], st)
+
+
+def svd_gpu_dev_raw(m, n, dA, lda, dsigma, dU, ldu, dV, ldv, stream):
+    lib().svd_gpu_dev(m, n, dA, lda, dsigma, dU, ldu, dV, ldv, stream)

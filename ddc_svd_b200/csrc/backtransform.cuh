@@ -1,0 +1,13 @@
+// backtransform.cuh — internal interface of the compact-WY back-transform (backtransform.cu)
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+namespace svdgpu {
+constexpr int WY_MAX_SPLIT = 16;
+// C (rows x nc, ldc, device) <- H_0 H_1 ... H_{nref-1} C with the reflectors stored in A
+// (device, lda) the way bidiag leaves them: left=1 column reflectors A[j:rows, j] (multU,
+// bidiag_par.c:1046-1095), left=0 row reflectors A[j, j+1:rows] (multV, :990-1043).
+size_t backtransform_workspace_bytes(int rows, int nref, int nc);
+void wy_apply_device(int left, int rows, int nref, const double *A, long lda, double *C, long ldc, int nc,
+                     void *workspace, cudaStream_t st);
+}

@@ -1,0 +1,478 @@
+// bidiag.cu — Golub-Kahan Householder bidiagonalization on sm_100a.
+//
+// Replaces the device half of the reference's bidiag_par() (bidiag_par.c:34-450) and its ten
+// OpenCL kernels (normsq_matcol/matrow, sum, update_scale_matcol/matrow, sanders,
+// left/right_dotprods, left/right_update_mat).  Same mathematics and the same stored
+// result — unit-2-norm reflectors v (H = I - 2 v v^T) left in place in A, alpha/beta with
+// the reference's sign rule (update_scale_matcol.cl:58-82) — but a different organisation:
+//
+//   * panel-deferred updates (the dlabrd idea): inside a panel of nb steps the trailing
+//     matrix is NOT rewritten; A_cur = A - V Y^T - X U^T is carried by four thin panels and
+//     the trailing block is updated once per panel by a rank-2nb FP64 DMMA GEMM.  Per step
+//     the trailing matrix is therefore only READ twice (the reference reads/writes it 6x).
+//   * per step exactly two streaming passes over the trailing matrix:
+//       gemvT:  t = A^T c   (column dots; warp per 4 columns, 128-bit loads down the column)
+//       gemvN:  t = A  r    (row dots; thread per 2 rows, 128-bit loads, columns unrolled x8)
+//     with the *unnormalised* current column c / row r, so that the norm, the sign and the
+//     scale of the reflector (normsq_* + sum + update_scale_* in the reference) are applied
+//     algebraically afterwards — no extra pass and no extra grid-wide dependency.
+//   * the panel dot products (V^T c, X^T c, Y^T r, U^T r) and the norms c.c / r.r ride along
+//     in extra CTAs of the same two launches.
+//   * two small elementwise kernels (finish_y, finish_x) turn the pass results into the new
+//     panel columns, write the reflectors in place and form the next column / row.
+// 4 launches per step (reference: 10-12), no host synchronisation inside the loop.
+#include "common.cuh"
+#include "bidiag.cuh"
+
+namespace svdgpu {
+
+constexpr int NBMAX = 64;
+constexpr int GT_CW = 4;          // columns per warp in gemvT
+constexpr int GT_WARPS = 8;
+constexpr int GN_THREADS = 256;   // each thread owns 2 rows in gemvN
+constexpr int GN_UNROLL = 8;
+
+// ---------------------------------------------------------------------------------------
+// block-wide dot of two strided-1 vectors (used by the "extra" CTAs)
+__device__ double block_dot(const double *__restrict__ x, const double *__restrict__ y, int len)
+{
+    double acc = 0.0;
+    int t = threadIdx.x;
+    int l4 = len & ~3;
+    for (int p = t * 4; p < l4; p += blockDim.x * 4) {
+        acc += x[p] * y[p] + x[p + 1] * y[p + 1] + x[p + 2] * y[p + 2] + x[p + 3] * y[p + 3];
+    }
+    for (int p = l4 + t; p < len; p += blockDim.x) acc += x[p] * y[p];
+    acc = warp_sum(acc);
+    __shared__ double red[32];
+    __syncthreads();
+    if ((t & 31) == 0) red[t >> 5] = acc;
+    __syncthreads();
+    double tot = 0.0;
+    if (t < 32) {
+        tot = (t < (int)(blockDim.x >> 5)) ? red[t] : 0.0;
+        tot = warp_sum(tot);
+    }
+    return tot;   // valid in warp 0
+}
+
+// ---------------------------------------------------------------------------------------
+// gemvT: tmp[s][j] = sum_{r in split s} A[r,j] * c[r]   for j in (i, n)
+//   grid.x = colGroups + nextra, grid.y = nsplit.  Extra CTAs (y == 0 only): panel dots
+//   dots[w] = P[:,w] . c  (w < k), dots[nb+w] = P[:,nb+w] . c (w < k), dots[2nb] = c . c,
+//   all over rows [i, m).
+__global__ void __launch_bounds__(GT_WARPS * 32)
+gemvT_kernel(const double *__restrict__ A, long lda, int i, int m, int n, int mpad,
+             const double *__restrict__ c, double *__restrict__ tmp, long ldt,
+             int colGroups, int rowsPerSplit,
+             const double *__restrict__ P, long ldp, int nb, int k, double *__restrict__ dots)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if ((int)blockIdx.x >= colGroups) {
+        if (blockIdx.y != 0) return;
+        int w = blockIdx.x - colGroups;                       // 0 .. 2k
+        const double *x = (w < k) ? P + (long)w * ldp : (w < 2 * k ? P + (long)(nb + w - k) * ldp : c);
+        int slot = (w < k) ? w : (w < 2 * k ? nb + (w - k) : 2 * nb);
+        double d = block_dot(x + i, c + i, m - i);
+        if (threadIdx.x == 0) dots[slot] = d;
+        return;
+    }
+    const int j0 = i + 1 + (blockIdx.x * GT_WARPS + warp) * GT_CW;
+    if (j0 >= n) return;
+    const int rbeg = (i & ~1) + blockIdx.y * rowsPerSplit;
+    const int rend = min(mpad, rbeg + rowsPerSplit);
+    const double *col[GT_CW];
+#pragma unroll
+    for (int q = 0; q < GT_CW; ++q) col[q] = A + (long)min(j0 + q, n - 1) * lda;
+    double acc[GT_CW];
+#pragma unroll
+    for (int q = 0; q < GT_CW; ++q) acc[q] = 0.0;
+
+    int r = rbeg + 2 * lane;
+    for (; r + 192 < rend; r += 256) {
+        double2 cv[4], av[4][GT_CW];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            cv[u] = *reinterpret_cast<const double2 *>(c + r + 64 * u);
+#pragma unroll
+            for (int q = 0; q < GT_CW; ++q) av[u][q] = ldg_stream2(col[q] + r + 64 * u);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int q = 0; q < GT_CW; ++q) acc[q] += av[u][q].x * cv[u].x + av[u][q].y * cv[u].y;
+    }
+    for (; r < rend; r += 64) {
+        double2 cv = *reinterpret_cast<const double2 *>(c + r);
+#pragma unroll
+        for (int q = 0; q < GT_CW; ++q) {
+            double2 av = ldg_stream2(col[q] + r);
+            acc[q] += av.x * cv.x + av.y * cv.y;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < GT_CW; ++q) {
+        double s = warp_sum(acc[q]);
+        if (lane == 0 && j0 + q < n) tmp[(long)blockIdx.y * ldt + j0 + q] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// gemvN: tmp[s][r] = sum_{j in split s} A[r,j] * rv[j]   for rows r >= rbase=(i+1)&~1
+//   grid.x = rowBlocks + nextra, grid.y = nsplit.  Extra CTAs: dots[w] = Q[:,w] . rv (w <= k),
+//   dots[nb+w] = Q[:,nb+w] . rv (w < k), dots[2nb] = rv . rv, over j in (i, n).
+__global__ void __launch_bounds__(GN_THREADS)
+gemvN_kernel(const double *__restrict__ A, long lda, int i, int m, int n, int mpad,
+             const double *__restrict__ rv, double *__restrict__ tmp, long ldt,
+             int rowBlocks, int colsPerSplit,
+             const double *__restrict__ Q, long ldq, int nb, int k, double *__restrict__ dots)
+{
+    if ((int)blockIdx.x >= rowBlocks) {
+        if (blockIdx.y != 0) return;
+        int w = blockIdx.x - rowBlocks;                       // 0 .. 2k+1
+        const double *x = (w <= k) ? Q + (long)w * ldq
+                                   : (w <= 2 * k ? Q + (long)(nb + w - k - 1) * ldq : rv);
+        int slot = (w <= k) ? w : (w <= 2 * k ? nb + (w - k - 1) : 2 * nb);
+        double d = block_dot(x + i + 1, rv + i + 1, n - i - 1);
+        if (threadIdx.x == 0) dots[slot] = d;
+        return;
+    }
+    extern __shared__ double s_rv[];
+    const int jbeg = i + 1 + blockIdx.y * colsPerSplit;
+    const int jend = min(n, jbeg + colsPerSplit);
+    if (jbeg >= jend) return;
+    for (int t = threadIdx.x; t < jend - jbeg; t += GN_THREADS) s_rv[t] = rv[jbeg + t];
+    __syncthreads();
+    const int r = ((i + 1) & ~1) + (blockIdx.x * GN_THREADS + threadIdx.x) * 2;
+    if (r >= mpad) return;
+    const double *a = A + r + (long)jbeg * lda;
+    double2 acc = make_double2(0.0, 0.0);
+    const int nc = jend - jbeg;
+    int j = 0;
+    for (; j + GN_UNROLL <= nc; j += GN_UNROLL) {
+        double2 av[GN_UNROLL];
+#pragma unroll
+        for (int u = 0; u < GN_UNROLL; ++u) av[u] = ldg_stream2(a + (long)(j + u) * lda);
+#pragma unroll
+        for (int u = 0; u < GN_UNROLL; ++u) {
+            double w = s_rv[j + u];
+            acc.x += av[u].x * w;
+            acc.y += av[u].y * w;
+        }
+    }
+    for (; j < nc; ++j) {
+        double2 av = ldg_stream2(a + (long)j * lda);
+        double w = s_rv[j];
+        acc.x += av.x * w;
+        acc.y += av.y * w;
+    }
+    *reinterpret_cast<double2 *>(tmp + (long)blockIdx.y * ldt + r) = acc;
+}
+
+// ---------------------------------------------------------------------------------------
+// The reflector recipe of the reference (update_scale_matcol.cl:45-82, bidiag.c:76-94)
+// expressed on the unnormalised vector: x0 first entry, nrm2 = x.x
+//   out = -s*nu ; v = (x + s*nu*e0) * inv ; inv = 1/(sqrt2*sqrt(nu^2+|nu*x0|))
+struct Refl { double snu, inv; };
+__device__ __forceinline__ Refl make_refl(double x0, double nrm2)
+{
+    Refl f;
+    double nu = sqrt(nrm2);
+    double s = (x0 < 0.0) ? -1.0 : 1.0;
+    f.snu = s * nu;
+    double sc = sqrt(2.0) * sqrt(nu * nu + fabs(nu * x0));
+    f.inv = (sc > 0.0) ? 1.0 / sc : 0.0;      // zero vector: H = I (the reference would NaN here)
+    return f;
+}
+
+// finish_y: after gemvT of step i (panel column k).
+__global__ void __launch_bounds__(256)
+finish_y_kernel(double *__restrict__ A, long lda, int i, int m, int n, int k, int nb, int do_col,
+                double *__restrict__ P, long ldp, double *__restrict__ Q, long ldq,
+                const double *__restrict__ c, double *__restrict__ rv,
+                const double *__restrict__ tmp, long ldt, int nsplit,
+                const double *__restrict__ dots, double *__restrict__ alpha)
+{
+    __shared__ double s_vTv[NBMAX], s_xTv[NBMAX], s_rowV[NBMAX], s_rowX[NBMAX];
+    const int t = threadIdx.x;
+    const double ci = c[i];
+    Refl f;
+    if (do_col) f = make_refl(ci, dots[2 * nb]); else { f.snu = 0.0; f.inv = 0.0; }
+    if (t < k) {
+        double pv = P[i + (long)t * ldp], px = P[i + (long)(nb + t) * ldp];
+        s_rowV[t] = pv;
+        s_rowX[t] = px;
+        s_vTv[t] = (dots[t] + f.snu * pv) * f.inv;
+        s_xTv[t] = (dots[nb + t] + f.snu * px) * f.inv;
+    }
+    if (t == 0 && blockIdx.x == 0) alpha[i] = do_col ? -f.snu : ci;
+    __syncthreads();
+    const double vi = (ci + f.snu) * f.inv;
+    const int idx = blockIdx.x * blockDim.x + t;
+    const int R = n - i - 1, L = m - i;
+    if (idx < R) {
+        const int j = i + 1 + idx;
+        const double aij = A[i + (long)j * lda];
+        double tt = 0.0;
+        if (do_col) for (int s = 0; s < nsplit; ++s) tt += tmp[(long)s * ldt + j];
+        double corr = 0.0, rr = aij;
+        for (int q = 0; q < k; ++q) {
+            double yk = Q[j + (long)q * ldq], uk = Q[j + (long)(nb + q) * ldq];
+            corr += yk * s_vTv[q] + uk * s_xTv[q];
+            rr -= s_rowV[q] * yk + s_rowX[q] * uk;
+        }
+        double y = do_col ? 2.0 * ((tt + f.snu * aij) * f.inv - corr) : 0.0;
+        Q[j + (long)k * ldq] = y;
+        rr -= vi * y;
+        rv[j] = rr;
+    }
+    if (idx < L) {
+        const int r = i + idx;
+        if (do_col) {
+            double v = (c[r] + (idx == 0 ? f.snu : 0.0)) * f.inv;
+            A[r + (long)i * lda] = v;
+            P[r + (long)k * ldp] = v;
+        } else {
+            if (idx == 0) A[r + (long)i * lda] = 0.0;     // bidiag.c:160-162 "no reflection on left"
+            P[r + (long)k * ldp] = 0.0;
+        }
+    }
+}
+
+// finish_x: after gemvN of step i.  Also forms the next current column c' (column i+1).
+__global__ void __launch_bounds__(256)
+finish_x_kernel(double *__restrict__ A, long lda, int i, int m, int n, int k, int nb, int do_row,
+                double *__restrict__ P, long ldp, double *__restrict__ Q, long ldq,
+                double *__restrict__ c, const double *__restrict__ rv,
+                const double *__restrict__ tmp, long ldt, int nsplit,
+                const double *__restrict__ dots, double *__restrict__ beta)
+{
+    __shared__ double s_yTu[NBMAX], s_uTu[NBMAX], s_rowY[NBMAX], s_rowU[NBMAX];
+    const int t = threadIdx.x;
+    const int R = n - i - 1, Lb = m - i - 1;
+    const double rf = (R > 0) ? rv[i + 1] : 0.0;
+    Refl f;
+    if (do_row) f = make_refl(rf, dots[2 * nb]); else { f.snu = 0.0; f.inv = 0.0; }
+    const double ufirst = do_row ? (rf + f.snu) * f.inv : 0.0;
+    if (R > 0) {
+        if (t <= k) {
+            double qy = Q[(i + 1) + (long)t * ldq];
+            s_rowY[t] = qy;
+            s_yTu[t] = (dots[t] + f.snu * qy) * f.inv;
+        }
+        if (t < k) {
+            double qu = Q[(i + 1) + (long)(nb + t) * ldq];
+            s_rowU[t] = qu;
+            s_uTu[t] = (dots[nb + t] + f.snu * qu) * f.inv;
+        }
+        if (t == 0 && blockIdx.x == 0) {
+            beta[i] = do_row ? -f.snu : rf;
+            if (!do_row) A[i + (long)(i + 1) * lda] = 0.0;    // bidiag.c:124-128
+        }
+    }
+    __syncthreads();
+    const int idx = blockIdx.x * blockDim.x + t;
+    if (R > 0 && idx < Lb) {
+        const int r = i + 1 + idx;
+        const double ar = A[r + (long)(i + 1) * lda];
+        double tt = 0.0;
+        if (do_row) for (int s = 0; s < nsplit; ++s) tt += tmp[(long)s * ldt + r];
+        double corr = 0.0, cc = ar;
+        for (int q = 0; q <= k; ++q) {
+            double vk = P[r + (long)q * ldp];
+            corr += vk * s_yTu[q];
+            cc -= vk * s_rowY[q];
+        }
+        for (int q = 0; q < k; ++q) {
+            double xk = P[r + (long)(nb + q) * ldp];
+            corr += xk * s_uTu[q];
+            cc -= xk * s_rowU[q];
+        }
+        double x = do_row ? 2.0 * ((tt + f.snu * ar) * f.inv - corr) : 0.0;
+        P[r + (long)(nb + k) * ldp] = x;
+        cc -= x * ufirst;
+        c[r] = cc;
+    }
+    if (idx == Lb) c[i] = 0.0;     // keeps the 128-bit loads of the next gemvT harmless
+    if (idx < R) {
+        const int j = i + 1 + idx;
+        double u = do_row ? (rv[j] + (idx == 0 ? f.snu : 0.0)) * f.inv : 0.0;
+        if (do_row) A[i + (long)j * lda] = u;
+        Q[j + (long)(nb + k) * ldq] = u;
+    }
+}
+
+__global__ void col_init_kernel(const double *__restrict__ A, int m, long lda, double *__restrict__ c)
+{
+    long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < lda) c[r] = (r < m) ? A[r] : 0.0;
+}
+
+// ---------------------------------------------------------------------------------------
+size_t bidiag_workspace_bytes(int m, int n, long lda)
+{
+    long ldq = round_up(n, 2);
+    size_t d = 0;
+    d += (size_t)lda * 2 * NBMAX;          // P
+    d += (size_t)ldq * 2 * NBMAX;          // Q
+    d += (size_t)lda;                      // c
+    d += (size_t)ldq + 2;                  // rv
+    d += (size_t)BIDIAG_MAX_SPLIT * ldq;   // tmpT
+    d += (size_t)BIDIAG_MAX_SPLIT * lda;   // tmpN
+    d += 2 * (2 * NBMAX + 2);              // dots
+    return d * sizeof(double);
+}
+
+struct BidiagBufs {
+    double *P, *Q, *c, *rv, *tmpT, *tmpN, *dots1, *dots2;
+    long ldp, ldq;
+};
+static BidiagBufs carve(void *workspace, int n, long lda)
+{
+    BidiagBufs b;
+    b.ldp = lda; b.ldq = round_up(n, 2);
+    double *w = (double *)workspace;
+    b.P = w;      w += (size_t)b.ldp * 2 * NBMAX;
+    b.Q = w;      w += (size_t)b.ldq * 2 * NBMAX;
+    b.c = w;      w += (size_t)lda;
+    b.rv = w;     w += (size_t)b.ldq + 2;
+    b.tmpT = w;   w += (size_t)BIDIAG_MAX_SPLIT * b.ldq;
+    b.tmpN = w;   w += (size_t)BIDIAG_MAX_SPLIT * lda;
+    b.dots1 = w;  w += 2 * NBMAX + 2;
+    b.dots2 = w;
+    return b;
+}
+
+// gemvT launch for step i with k panel columns; returns the number of row splits written
+static int launch_gemvT(const double *A, long lda, int i, int m, int n, int mpad, const BidiagBufs &b,
+                        int nb, int k, int target, cudaStream_t st)
+{
+    const int R = n - i - 1;
+    int colGroups = (R > 0) ? ceil_div(R, GT_WARPS * GT_CW) : 0;
+    int rows = mpad - (i & ~1);
+    int rowsPerSplit = rows, nsplit = 1;
+    if (colGroups > 0) {
+        nsplit = target / colGroups;
+        if (nsplit < 1) nsplit = 1;
+        if (nsplit > BIDIAG_MAX_SPLIT) nsplit = BIDIAG_MAX_SPLIT;
+        rowsPerSplit = (int)round_up(ceil_div(rows, nsplit), 256);
+        nsplit = ceil_div(rows, rowsPerSplit);
+    }
+    dim3 grid(colGroups + 2 * k + 1, nsplit);
+    gemvT_kernel<<<grid, GT_WARPS * 32, 0, st>>>(A, lda, i, m, n, mpad, b.c, b.tmpT, b.ldq, colGroups,
+                                                 rowsPerSplit, b.P, b.ldp, nb, k, b.dots1);
+    SVD_KERNEL_CHECK();
+    return colGroups == 0 ? 0 : nsplit;
+}
+
+static int launch_gemvN(const double *A, long lda, int i, int m, int n, int mpad, const BidiagBufs &b,
+                        int nb, int k, int target, cudaStream_t st)
+{
+    const int R = n - i - 1, Lb = m - i - 1;
+    int rows = (Lb > 0) ? mpad - ((i + 1) & ~1) : 0;
+    int rowBlocks = (rows > 0) ? ceil_div(rows, 2 * GN_THREADS) : 0;
+    int colsPerSplit = R > 0 ? R : 1, nsplit = 1;
+    if (rowBlocks > 0) {
+        nsplit = target / rowBlocks;
+        if (nsplit < 1) nsplit = 1;
+        if (nsplit > BIDIAG_MAX_SPLIT) nsplit = BIDIAG_MAX_SPLIT;
+        colsPerSplit = (int)round_up(ceil_div(R, nsplit), 32);
+        if (colsPerSplit > 4096) colsPerSplit = 4096;           // smem staging of r
+        nsplit = ceil_div(R, colsPerSplit);
+        if (nsplit > BIDIAG_MAX_SPLIT) {                        // extremely wide: bigger chunks
+            nsplit = BIDIAG_MAX_SPLIT;
+            colsPerSplit = (int)round_up(ceil_div(R, nsplit), 32);
+            nsplit = ceil_div(R, colsPerSplit);
+        }
+    }
+    dim3 grid(rowBlocks + 2 * k + 2, nsplit);
+    size_t smem = sizeof(double) * (size_t)colsPerSplit;
+    if (smem > 48 * 1024)
+        SVD_CUDA_CHECK(cudaFuncSetAttribute(gemvN_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)smem));
+    gemvN_kernel<<<grid, GN_THREADS, smem, st>>>(A, lda, i, m, n, mpad, b.rv, b.tmpN, lda, rowBlocks,
+                                                 colsPerSplit, b.Q, b.ldq, nb, k, b.dots2);
+    SVD_KERNEL_CHECK();
+    return rowBlocks == 0 ? 0 : nsplit;
+}
+
+static void sm_targets(int &targetT, int &targetN)
+{
+    int dev = 0, nsm = 148;
+    SVD_CUDA_CHECK(cudaGetDevice(&dev));
+    SVD_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    targetT = nsm * 4; targetN = nsm * 8;
+}
+
+void bidiag_device(int m, int n, double *A, long lda, double *alpha, double *beta, void *workspace,
+                   int nb, cudaStream_t st)
+{
+    if (nb <= 0 || nb > NBMAX) nb = 32;
+    const int mn = (m < n) ? m : n;
+    const int mpad = (int)round_up(m, 2);
+    if (lda < mpad || (lda & 1)) {
+        fprintf(stderr, "bidiag_device: lda (%ld) must be even and >= round_up(m,2)\n", lda);
+        abort();
+    }
+    const BidiagBufs b = carve(workspace, n, lda);
+    int targetT, targetN;
+    sm_targets(targetT, targetN);
+
+    SVD_CUDA_CHECK(cudaMemsetAsync(b.rv, 0, sizeof(double) * ((size_t)b.ldq + 2), st));
+    SVD_CUDA_CHECK(cudaMemsetAsync(b.dots1, 0, sizeof(double) * 2 * (2 * NBMAX + 2), st));
+    col_init_kernel<<<ceil_div(lda, 256), 256, 0, st>>>(A, m, lda, b.c);
+    SVD_KERNEL_CHECK();
+
+    int k = 0;
+    for (int i = 0; i < mn; ++i) {              // steps 0..mn-2 regular, step mn-1 is the tail
+        const bool tail = (i == mn - 1);
+        const int do_col = tail ? (n >= m + 1 ? 0 : 1) : 1;
+        const int do_row = tail ? (n >= m + 1 ? 1 : 0) : (i < n - 2 ? 1 : 0);
+        const int R = n - i - 1, Lb = m - i - 1;
+        int nsplitT = 0, nsplitN = 0;
+
+        if (do_col) nsplitT = launch_gemvT(A, lda, i, m, n, mpad, b, nb, k, targetT, st);
+        {
+            int work = (R > m - i) ? R : (m - i);
+            finish_y_kernel<<<ceil_div(work, 256), 256, 0, st>>>(A, lda, i, m, n, k, nb, do_col, b.P, b.ldp,
+                                                                 b.Q, b.ldq, b.c, b.rv, b.tmpT, b.ldq,
+                                                                 nsplitT, b.dots1, alpha);
+            SVD_KERNEL_CHECK();
+        }
+        if (tail && !do_row) break;             // tall/square tail: last column reflector only
+        if (do_row) nsplitN = launch_gemvN(A, lda, i, m, n, mpad, b, nb, k, targetN, st);
+        {
+            int work = (R > Lb + 1) ? R : (Lb + 1);
+            finish_x_kernel<<<ceil_div(work, 256), 256, 0, st>>>(A, lda, i, m, n, k, nb, do_row, b.P, b.ldp,
+                                                                 b.Q, b.ldq, b.c, b.rv, b.tmpN, lda, nsplitN,
+                                                                 b.dots2, beta);
+            SVD_KERNEL_CHECK();
+        }
+        ++k;
+        if (k == nb && i + 1 < mn) {
+            // trailing update: A[i+1:, i+1:] -= [V|X][i+1:, :] * [Y|U][i+1:, :]^T
+            // (the panel layout keeps V at columns [0,nb) and X at [nb,2nb) => one K = 2nb GEMM)
+            GemmArgs g = {};
+            g.M = m - i - 1; g.N = n - i - 1; g.K = 2 * nb;
+            g.A = b.P + (i + 1); g.lda = b.ldp; g.transA = 0;
+            g.B = b.Q + (i + 1); g.ldb = b.ldq; g.transB = 1;
+            g.C = A + (i + 1) + (long)(i + 1) * lda; g.ldc = lda;
+            g.alpha = -1.0; g.beta = 1.0; g.batch = 1; g.splitk = 1;
+            dgemm_dmma(g, st);
+            k = 0;
+        }
+    }
+}
+
+// One streaming pass over the full matrix (step 0, empty panel), for roofline measurements.
+void bidiag_pass_probe(int m, int n, const double *A, long lda, void *workspace, int which, cudaStream_t st)
+{
+    const int mpad = (int)round_up(m, 2);
+    const BidiagBufs b = carve(workspace, n, lda);
+    int targetT, targetN;
+    sm_targets(targetT, targetN);
+    if (which == 0) launch_gemvT(A, lda, 0, m, n, mpad, b, 32, 0, targetT, st);
+    else            launch_gemvN(A, lda, 0, m, n, mpad, b, 32, 0, targetN, st);
+}
+
+} // namespace svdgpu

@@ -1,0 +1,17 @@
+// bidiag.cuh — internal interface of the bidiagonalization phase (bidiag.cu)
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+namespace svdgpu {
+constexpr int BIDIAG_MAX_SPLIT = 64;
+// A: m x n column-major on the device, leading dimension lda (even, >= round_up(m,2); rows
+// [m, lda) must hold finite values).  On return A holds the reflectors exactly as the
+// reference's bidiag_par() leaves them (bidiag_par.c:310-397), alpha[min(m,n)],
+// beta[n-1 if m >= n else m].  All work is enqueued on `st`; no host synchronisation.
+size_t bidiag_workspace_bytes(int m, int n, long lda);
+void bidiag_device(int m, int n, double *A, long lda, double *alpha, double *beta, void *workspace,
+                   int nb, cudaStream_t st);
+// which = 0: one gemvT pass, 1: one gemvN pass over the full matrix (workspace as above; its
+// vector buffers must have been initialised, e.g. by a previous bidiag_device call or a memset)
+void bidiag_pass_probe(int m, int n, const double *A, long lda, void *workspace, int which, cudaStream_t st);
+}

@@ -1,0 +1,269 @@
+// twisted.cu — singular vectors of the bidiagonal by twisted factorizations on sm_100a.
+//
+// Replaces the host/OpenMP phase CalcRightSingularVectors / RighttoLeftSingularVectors
+// (parallel-twisted.c:554-637, :530-551): SquareB (:290-316), CholFactorization (:320-362),
+// TwistedFactorization (:431-528, with which_min_gamma :240-288), backsolve (:365-427),
+// NormalizeVectors (:88-123), BidiagMatVec (:58-86).
+//
+// Same method — for every sigma factor B^T B - sigma^2 I from the top (forward) and from the
+// bottom (backward), twist the two factorizations where |gamma| is smallest and solve
+// N_k x = e_k outward from the twist — with three changes:
+//   * the factorizations are the differential qd transforms dstqds / dpqds of
+//     B^T B = L diag(a^2) L^T (no tridiagonal is formed; parallel-twisted.c:304-314 squares B
+//     and runs plain LDL^T, which is what costs the reference its orthogonality);
+//   * instead of the reference's extra solve with the twist pinned at m/2 (:392-424) one
+//     Rayleigh-quotient correction  sigma^2 += gamma_k / ||z||^2  is applied and the vector is
+//     recomputed (gamma_k and ||z||^2 are by-products);
+//   * none of the reference's six n x m work arrays survive; two scratch panels in a
+//     [position][sigma] layout are reused in place.
+//
+// Mapping: ONE LANE PER SINGULAR VALUE.  The recurrences are serial in the position index j
+// (one divide per step) and independent across sigma, so a warp advances 32 sigmas in
+// lock-step with fully coalesced scratch traffic; forward and backward sweeps (and later the
+// two halves of the outward solve) run concurrently in different CTAs.  A CTA-per-sigma
+// mapping would issue the same recurrences with 1 of 32 lanes active.
+#include "common.cuh"
+#include "twisted.cuh"
+#include <cfloat>
+
+namespace svdgpu {
+
+__global__ void tw_prep_kernel(int n, int mb, const double *__restrict__ a, const double *__restrict__ b,
+                               double *__restrict__ q, double *__restrict__ e, double *__restrict__ ab,
+                               double *__restrict__ pivmin)
+{
+    __shared__ double red[32];
+    double mx = 0.0;
+    for (int j = threadIdx.x; j < mb; j += blockDim.x) {
+        double aj = (j < n) ? a[j] : 0.0;
+        double bj = (j < mb - 1) ? b[j] : 0.0;
+        q[j] = aj * aj; e[j] = bj * bj; ab[j] = aj * bj;
+        mx = fmax(mx, fmax(aj * aj, bj * bj));
+    }
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = fmax(mx, red[w]);
+        *pivmin = fmax(mx, 1.0) * 1e-290;
+    }
+}
+
+__global__ void tw_tau_init_kernel(int ns, const double *__restrict__ sigma, double *__restrict__ tau)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < ns) tau[t] = sigma[t] * sigma[t];
+}
+
+__device__ __forceinline__ double guard_pivot(double d, double pivmin)
+{
+    return (fabs(d) < pivmin) ? -pivmin : d;
+}
+
+// blockIdx.y == 0: dstqds  s_0 = -tau ; d+_j = q_j + s_j ; s_{j+1} = s_j e_j / d+_j - tau
+// blockIdx.y == 1: dpqds   p_{m-1} = q_{m-1} - tau ; d-_{j+1} = e_j + p_{j+1} ; p_j = p_{j+1} q_j / d-_{j+1} - tau
+__global__ void __launch_bounds__(32)
+tw_qd_kernel(int mb, int ns, const double *__restrict__ q, const double *__restrict__ e,
+             const double *__restrict__ tau, const double *__restrict__ pivmin_p,
+             double *__restrict__ S, double *__restrict__ P)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ns) return;
+    const double tv = tau[t], pivmin = *pivmin_p;
+    if (blockIdx.y == 0) {
+        double s = -tv;
+#pragma unroll 4
+        for (int j = 0; j < mb; ++j) {
+            S[(size_t)j * ns + t] = s;
+            double dp = guard_pivot(__ldg(q + j) + s, pivmin);
+            s = s * (__ldg(e + j) / dp) - tv;
+        }
+    } else {
+        double p = __ldg(q + mb - 1) - tv;
+        P[(size_t)(mb - 1) * ns + t] = p;
+#pragma unroll 4
+        for (int j = mb - 2; j >= 0; --j) {
+            double dm = guard_pivot(__ldg(e + j) + p, pivmin);
+            p = p * (__ldg(q + j) / dm) - tv;
+            P[(size_t)j * ns + t] = p;
+        }
+    }
+}
+
+// gamma_j = s_j + p_j + tau; twist index = argmin |gamma_j|, later index on ties
+// (which_min_gamma, parallel-twisted.c:277-284)
+__global__ void __launch_bounds__(64)
+tw_select_kernel(int mb, int ns, const double *__restrict__ tau, const double *__restrict__ S,
+                 const double *__restrict__ P, int *__restrict__ kidx, double *__restrict__ gk)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ns) return;
+    const double tv = tau[t];
+    double best = DBL_MAX, bestg = 0.0;
+    int bk = 0;
+#pragma unroll 8
+    for (int j = 0; j < mb; ++j) {
+        double g = S[(size_t)j * ns + t] + P[(size_t)j * ns + t] + tv;
+        double ag = fabs(g);
+        if (ag <= best) { best = ag; bestg = g; bk = j; }
+    }
+    kidx[t] = bk;
+    gk[t] = bestg;
+}
+
+// z_k = 1; j < k: z_j = -(ab_j / d+_j) z_{j+1};  j >= k: z_{j+1} = -(ab_j / d-_{j+1}) z_j
+// (TwistedFactorization, parallel-twisted.c:495-521).  z overwrites S in place.
+__global__ void __launch_bounds__(32)
+tw_solve_kernel(int mb, int ns, const double *__restrict__ q, const double *__restrict__ e,
+                const double *__restrict__ ab, const double *__restrict__ pivmin_p,
+                const int *__restrict__ kidx, double *__restrict__ S, const double *__restrict__ P,
+                double *__restrict__ nrm2)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ns) return;
+    const int k = kidx[t];
+    const double pivmin = *pivmin_p;
+    double z = 1.0, acc = 0.0;
+    if (blockIdx.y == 0) {
+        for (int j = k - 1; j >= 0; --j) {
+            double dp = guard_pivot(__ldg(q + j) + S[(size_t)j * ns + t], pivmin);
+            z = -(__ldg(ab + j) / dp) * z;
+            S[(size_t)j * ns + t] = z;
+            acc += z * z;
+        }
+        S[(size_t)k * ns + t] = 1.0;
+        nrm2[t] = acc + 1.0;
+    } else {
+        for (int j = k; j < mb - 1; ++j) {
+            double dm = guard_pivot(__ldg(e + j) + P[(size_t)(j + 1) * ns + t], pivmin);
+            z = -(__ldg(ab + j) / dm) * z;
+            S[(size_t)(j + 1) * ns + t] = z;
+            acc += z * z;
+        }
+        nrm2[ns + t] = acc;
+    }
+}
+
+// Rayleigh-quotient correction tau += gamma_k/||z||^2, accepted only while sigma stays
+// between the midpoints to its neighbours.
+__global__ void tw_rqi_kernel(int ns, int i0, int ntot, const double *__restrict__ sigma_all,
+                              const double *__restrict__ gk, const double *__restrict__ nrm2,
+                              double *__restrict__ tau)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ns) return;
+    double nn = nrm2[t] + nrm2[ns + t];
+    double tn = tau[t] + gk[t] / nn;
+    int gi = i0 + t;
+    double s = sigma_all[gi];
+    double lo = (gi > 0) ? 0.5 * (sigma_all[gi - 1] + s) : 0.0;
+    double hi = (gi + 1 < ntot) ? 0.5 * (sigma_all[gi + 1] + s) : DBL_MAX;
+    if (tn > 0.0) {
+        double sn = sqrt(tn);
+        if (sn >= lo && sn <= hi) tau[t] = tn;
+    }
+}
+
+// normalise, transpose to the reference's layout X[i*mb + j] (NormalizeVectors :106-120) and
+// form y = B x / sigma, Y[i*n + j] (BidiagMatVec :75-84, RighttoLeftSingularVectors :545-549)
+__global__ void __launch_bounds__(256)
+tw_finalize_kernel(int n, int mb, int ns, const double *__restrict__ a, const double *__restrict__ b,
+                   const double *__restrict__ tau, const double *__restrict__ Z,
+                   const double *__restrict__ nrm2, double *__restrict__ X, long ldx,
+                   double *__restrict__ Y, long ldy, double *__restrict__ sigma_out)
+{
+    __shared__ double tile[33][33];
+    const int t0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+    // load 33 positions (one halo row) x 32 sigmas, scaled
+    for (int r = ty; r < 33; r += 8) {
+        int j = j0 + r, t = t0 + tx;
+        double v = 0.0;
+        if (j < mb && t < ns) v = Z[(size_t)j * ns + t] * rsqrt(nrm2[t] + nrm2[ns + t]);
+        tile[r][tx] = v;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        int t = t0 + r, j = j0 + tx;
+        if (t >= ns) continue;
+        double xj = tile[tx][r], xj1 = tile[tx + 1][r];
+        if (j < mb) X[(size_t)t * ldx + j] = xj;
+        if (Y != nullptr && j < n) {
+            double sg = sqrt(tau[t]);
+            double bj = (j < mb - 1) ? b[j] : 0.0;
+            double y = a[j] * xj + bj * xj1;
+            Y[(size_t)t * ldy + j] = (sg > 0.0) ? y / sg : 0.0;
+        }
+    }
+    if (blockIdx.y == 0 && threadIdx.x < 32 && sigma_out != nullptr) {
+        int t = t0 + threadIdx.x;
+        if (t < ns) sigma_out[t] = sqrt(tau[t]);
+    }
+}
+
+static int tw_chunk(int mb, int ns)
+{
+    const size_t budget = (size_t)4 << 30;                 // bytes for the two scratch panels
+    long c = (long)(budget / (2 * sizeof(double) * (size_t)mb));
+    c = c / 32 * 32;
+    if (c < 32) c = 32;
+    if (c > ns) c = ns;
+    return (int)c;
+}
+
+size_t twisted_workspace_bytes(int n, int mb, int ns)
+{
+    int c = tw_chunk(mb, ns);
+    size_t d = 0;
+    d += 3 * (size_t)mb + 8;            // q, e, ab, pivmin
+    d += 2 * (size_t)mb * c;            // S, P
+    d += 4 * (size_t)c + 8;             // tau, gk, nrm2[2]
+    return d * sizeof(double) + (size_t)c * sizeof(int) + 4096;
+}
+
+void twisted_vectors_device(int n, int mb, const double *a, const double *b, const double *sigma_all,
+                            int ntot, int i0, int ns, double *X, long ldx, double *Y, long ldy,
+                            double *sigma_out, int rqi_steps, void *workspace, cudaStream_t st)
+{
+    if (ns <= 0) return;
+    const int cmax = tw_chunk(mb, ns);
+    double *w = (double *)workspace;
+    double *q = w;       w += mb;
+    double *e = w;       w += mb;
+    double *ab = w;      w += mb;
+    double *pivmin = w;  w += 8;
+    double *S = w;       w += (size_t)mb * cmax;
+    double *P = w;       w += (size_t)mb * cmax;
+    double *tau = w;     w += cmax;
+    double *gk = w;      w += cmax;
+    double *nrm2 = w;    w += 2 * (size_t)cmax + 8;
+    int *kidx = (int *)w;
+
+    tw_prep_kernel<<<1, 1024, 0, st>>>(n, mb, a, b, q, e, ab, pivmin);
+    SVD_KERNEL_CHECK();
+    for (int c0 = 0; c0 < ns; c0 += cmax) {
+        const int c = (ns - c0 < cmax) ? ns - c0 : cmax;
+        const int gi0 = i0 + c0;
+        tw_tau_init_kernel<<<ceil_div(c, 256), 256, 0, st>>>(c, sigma_all + gi0, tau);
+        SVD_KERNEL_CHECK();
+        for (int sweep = 0; sweep <= rqi_steps; ++sweep) {
+            tw_qd_kernel<<<dim3(ceil_div(c, 32), 2), 32, 0, st>>>(mb, c, q, e, tau, pivmin, S, P);
+            SVD_KERNEL_CHECK();
+            tw_select_kernel<<<ceil_div(c, 64), 64, 0, st>>>(mb, c, tau, S, P, kidx, gk);
+            SVD_KERNEL_CHECK();
+            tw_solve_kernel<<<dim3(ceil_div(c, 32), 2), 32, 0, st>>>(mb, c, q, e, ab, pivmin, kidx, S, P, nrm2);
+            SVD_KERNEL_CHECK();
+            if (sweep < rqi_steps) {
+                tw_rqi_kernel<<<ceil_div(c, 256), 256, 0, st>>>(c, gi0, ntot, sigma_all, gk, nrm2, tau);
+                SVD_KERNEL_CHECK();
+            }
+        }
+        dim3 grid(ceil_div(c, 32), ceil_div(mb, 32));
+        tw_finalize_kernel<<<grid, 256, 0, st>>>(n, mb, c, a, b, tau, S, nrm2, X + (size_t)c0 * ldx, ldx,
+                                                 Y ? Y + (size_t)c0 * ldy : nullptr, ldy,
+                                                 sigma_out ? sigma_out + c0 : nullptr);
+        SVD_KERNEL_CHECK();
+    }
+}
+
+} // namespace svdgpu

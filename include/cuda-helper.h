@@ -1,0 +1,81 @@
+/* cuda-helper.h — thin C-ABI device layer of libsvdgpu.so (plain pointers and sizes only).
+ *
+ * This is what replaces the reference's OpenCL glue cl-helper.c / cl-helper.h:
+ *   create_context_on (cl-helper.h:99-101)        -> svdgpu_set_device / svdgpu_stream_create
+ *   clCreateBuffer / clReleaseMemObject            -> svdgpu_malloc / svdgpu_free
+ *   clEnqueueWriteBuffer / clEnqueueReadBuffer     -> svdgpu_h2d / svdgpu_d2h (+ _2d)
+ *   clFinish                                       -> svdgpu_stream_sync
+ *   CHECK_CL_ERROR / CALL_CL_GUARDED (:47-69)      -> every entry point aborts on CUDA errors
+ *   read_file + kernel_from_string + SET_n_KERNEL_ARGS + clEnqueueNDRangeKernel
+ *                                                  -> one launcher per kernel family below
+ * All `stream` arguments are cudaStream_t passed as void* (NULL = the legacy default stream);
+ * all d* pointers are device pointers.  Launchers only enqueue work unless stated.
+ */
+#ifndef SVDGPU_CUDA_HELPER_H
+#define SVDGPU_CUDA_HELPER_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- device / memory / stream glue -------------------------------------------------- */
+int    svdgpu_device_count(void);
+void   svdgpu_set_device(int dev);
+int    svdgpu_get_device(void);
+const char *svdgpu_device_name(void);           /* static buffer, current device */
+void  *svdgpu_malloc(size_t bytes);             /* stream-ordered pool allocation, aborts on failure */
+void   svdgpu_free(void *dptr);
+void   svdgpu_memset(void *dptr, int value, size_t bytes, void *stream);
+void   svdgpu_h2d(void *dst, const void *src, size_t bytes, void *stream);
+void   svdgpu_d2h(void *dst, const void *src, size_t bytes, void *stream);
+void   svdgpu_d2d(void *dst, const void *src, size_t bytes, void *stream);
+void   svdgpu_h2d_2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width_bytes,
+                     size_t height, void *stream);
+void   svdgpu_d2h_2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width_bytes,
+                     size_t height, void *stream);
+void  *svdgpu_stream_create(void);
+void   svdgpu_stream_destroy(void *stream);
+void   svdgpu_stream_sync(void *stream);
+void   svdgpu_stream_wait_event(void *stream, void *event);
+void  *svdgpu_event_create(void);
+void   svdgpu_event_destroy(void *event);
+void   svdgpu_event_record(void *event, void *stream);
+float  svdgpu_event_elapsed_ms(void *start, void *stop);   /* synchronises on stop */
+void  *svdgpu_host_alloc(size_t bytes);         /* pinned host memory */
+void   svdgpu_host_free(void *p);
+
+/* ---- kernel families (one launcher each) -------------------------------------------- */
+/* Householder bidiagonalization (bidiag_par.c:34-450 + its 10 .cl kernels).
+ * dA: m x n, lda even and >= m (rows [m,lda) finite); dalpha[min(m,n)], dbeta[n-1 | m]. */
+size_t svdgpu_bidiag_workspace(int m, int n, long lda);
+void   svdgpu_bidiag(int m, int n, double *dA, long lda, double *dalpha, double *dbeta,
+                     void *dwork, int nb, void *stream);
+/* dDC singular values (Calculations-Parallel.c:852-874); b1,b2 of length N; synchronises. */
+size_t svdgpu_ddc_workspace(int N);
+void   svdgpu_ddc_values(int N, const double *db1, const double *db2, double *dsigma,
+                         void *dwork, void *stream);
+/* twisted-factorization vectors for sigma_all[i0 .. i0+ns) (parallel-twisted.c:554-637,
+ * :530-551); X[t*ldx + j], j < mb; Y[t*ldy + j], j < n (Y may be NULL). */
+size_t svdgpu_twisted_workspace(int n, int mb, int ns);
+void   svdgpu_twisted_vectors(int n, int mb, const double *da, const double *db,
+                              const double *dsigma_all, int ntot, int i0, int ns,
+                              double *dX, long ldx, double *dY, long ldy, double *dsigma_out,
+                              int rqi_steps, void *dwork, void *stream);
+/* compact-WY back-transform (multU / multV, bidiag_par.c:990-1095):
+ * C(rows x nc) <- H_0 ... H_{nref-1} C, reflectors read from dA_mod. */
+size_t svdgpu_backtransform_workspace(int rows, int nref, int nc);
+void   svdgpu_wy_apply(int left, int rows, int nref, const double *dA_mod, long lda, double *dC,
+                       long ldc, int nc, void *dwork, void *stream);
+/* FP64 DMMA GEMM building block: C = beta*C + alpha*op(A)*op(B), column-major */
+void   svdgpu_dgemm(int transA, int transB, int M, int N, int K, double alpha, const double *dA,
+                    long lda, const double *dB, long ldb, double beta, double *dC, long ldc,
+                    void *stream);
+/* one gemvT + one gemvN pass over the full m x n matrix (the two streaming kernels of the
+ * bidiagonalization), for roofline measurement; returns nothing, only enqueues. */
+void   svdgpu_bidiag_pass_probe(int m, int n, const double *dA, long lda, void *dwork, int which,
+                                void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,112 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every declared symbol, the
+headers declare what the reference's client includes, the numpy model of the device numerics
+meets the north-star bounds, and the host helper functions behave like the reference's."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import util
+from util import p
+
+ROOT = util.ROOT
+INC = os.path.join(ROOT, "include")
+
+
+def _declared_symbols():
+    names = set()
+    for h in sorted(os.listdir(INC)):
+        txt = open(os.path.join(INC, h)).read()
+        txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+        for m in re.finditer(r"^\s*(?:const\s+)?(?:void|int|float|double|size_t|char)\s*\*?\s*\*?\s*(\w+)\s*\(", txt, re.M):
+            names.add(m.group(1))
+    return names
+
+
+def test_library_exports_every_declared_symbol():
+    import ddc_svd_b200 as D
+    assert os.path.exists(D.LIB_PATH), "libsvdgpu.so not built: run make / __graft_entry__.build()"
+    out = subprocess.check_output(["nm", "-D", "--defined-only", D.LIB_PATH]).decode()
+    exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
+    declared = _declared_symbols()
+    assert len(declared) > 50
+    missing = sorted(declared - exported)
+    assert not missing, f"declared in include/*.h but not exported: {missing}"
+    # the ctypes table binds the same set (AttributeError inside lib() would mean a gap)
+    D.lib()
+    assert {s[0] for s in D.SIGNATURES} == declared
+
+
+def test_reference_entry_point_signature():
+    txt = open(os.path.join(INC, "svd_gpu.h")).read()
+    assert "#ifndef SVDGPU" in txt
+    assert re.search(r"void\s+svd_gpu\(int m, int n, double\* A,double \* sigma, double \* U, double\* V\);", txt)
+    for h in ("cl-helper.h", "matrix_helper.h", "svd_gpu.h"):          # test-whole-svd.c:4-7
+        assert os.path.exists(os.path.join(INC, h))
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/test-whole-svd.c"), reason="reference not mounted")
+def test_dropin_client_links_unmodified():
+    subprocess.check_call(["make", "-C", ROOT, "dropin"], stdout=subprocess.DEVNULL)
+    assert os.path.exists(os.path.join(ROOT, "build", "test-whole-svd"))
+
+
+def test_host_helpers_match_reference_semantics():
+    import ddc_svd_b200 as D
+    L = D.lib()
+    rng = np.random.default_rng(3)
+    M, N, K = 7, 5, 4
+    A = np.asfortranarray(rng.standard_normal((M, N)))
+    AT = np.zeros((N, M), order="F")
+    L.transpose(M, N, p(A), p(AT))
+    assert np.array_equal(AT, A.T)
+    B = np.asfortranarray(rng.standard_normal((N, K)))
+    C = np.asfortranarray(rng.standard_normal((M, K)))
+    C0 = C.copy()
+    L.dgemm_simple(M, K, N, p(A), p(B), p(C))                 # accumulates into C
+    assert np.allclose(C, C0 + A @ B)
+    al = rng.standard_normal(4); be = rng.standard_normal(4)
+    Bm = np.zeros((4, 6), order="F")
+    L.form_bidiag(4, 6, p(al), p(be), p(Bm))
+    assert np.array_equal(Bm, util.bidiag_dense(al, be, 6))
+    Bm = np.zeros((6, 4), order="F")
+    L.form_bidiag(6, 4, p(al), p(be), p(Bm))
+    ref = np.zeros((6, 4)); ref[:4, :4] = util.bidiag_dense(al, be[:3])
+    assert np.array_equal(Bm, ref)
+    assert np.isclose(L.l2_norm_mat(M, N, p(A)), np.linalg.norm(A))
+    assert np.isclose(L.dot_prod(5, p(al.copy()[:4].repeat(2)[:5].copy()), p(np.ones(5))), al[:4].repeat(2)[:5].sum())
+    assert np.isclose(L.l2_norm_mat_row(M, N, N, p(A)), np.linalg.norm(A[0, :]))
+
+
+def test_compute_entry_fails_loudly_without_gpu():
+    # no CPU fallback: on a machine without CUDA the library must abort, not compute
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    code = ("import sys; sys.path.insert(0, %r); import numpy as np, ddc_svd_b200 as D; "
+            "D.svd_gpu(np.ones((4,4)))") % ROOT
+    r = subprocess.run(["python", "-c", code], capture_output=True)
+    assert r.returncode != 0
+    assert b"no usable CUDA device" in r.stderr or b"failed with error" in r.stderr
+
+
+@pytest.mark.parametrize("n", [40, 150])
+def test_device_numerics_model_meets_bounds(n):
+    # executable specification of the kernels' numerics (tests/model_numerics.py)
+    import model_numerics as mn
+    A = util.rand_matrix(n, n)
+    _, al, be = util.oracle_bidiag(A)
+    bep = np.zeros(n); bep[: n - 1] = be
+    B = util.bidiag_dense(al, be)
+    sv = np.linalg.svd(B, compute_uv=False)[::-1]
+    sig = mn.ddc_values(al, bep)
+    assert np.abs(sig - sv).max() / sv.max() < 10 * util.EPS * n
+    with np.errstate(all="ignore"):
+        X, sig2 = mn.twisted_vectors(al, be, sig)
+    Y = mn.left_from_right(al, be, sig2, X)
+    c = 100 * util.EPS * n
+    assert np.linalg.norm(X @ X.T - np.eye(n)) < c
+    assert np.linalg.norm(Y @ Y.T - np.eye(n)) < c
+    assert np.linalg.norm(B - Y.T @ np.diag(sig2) @ X) / np.linalg.norm(B) < c
