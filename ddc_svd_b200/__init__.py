@@ -83,6 +83,7 @@ SIGNATURES = [
     ("svdgpu_event_destroy", None, [c_void_p]),
     ("svdgpu_event_record", None, [c_void_p, c_void_p]),
     ("svdgpu_event_elapsed_ms", ctypes.c_float, [c_void_p, c_void_p]),
+    ("svdgpu_launch_count", ctypes.c_ulonglong, []),
     ("svdgpu_host_alloc", c_void_p, [c_size_t]),
     ("svdgpu_host_free", None, [c_void_p]),
     ("svdgpu_bidiag_workspace", c_size_t, [c_int, c_int, c_long]),

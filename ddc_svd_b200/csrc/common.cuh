@@ -17,7 +17,10 @@
         }                                                                                 \
     } while (0)
 
-#define SVD_KERNEL_CHECK() SVD_CUDA_CHECK(cudaGetLastError())
+// every kernel launch site is followed by SVD_KERNEL_CHECK(); it also counts the launch so that
+// bench.py can report how many of OUR kernels ran inside a timed region (svdgpu_launch_count)
+extern unsigned long long g_svdgpu_launches;
+#define SVD_KERNEL_CHECK() do { ++g_svdgpu_launches; SVD_CUDA_CHECK(cudaGetLastError()); } while (0)
 
 static inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 static inline long round_up(long a, long b) { return (a + b - 1) / b * b; }

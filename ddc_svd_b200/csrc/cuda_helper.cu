@@ -12,6 +12,7 @@
 #include "../../include/cuda-helper.h"
 
 using namespace svdgpu;
+unsigned long long g_svdgpu_launches = 0;
 static inline cudaStream_t S(void *s) { return (cudaStream_t)s; }
 
 extern "C" {
@@ -109,6 +110,8 @@ void *svdgpu_host_alloc(size_t bytes)
     return p;
 }
 void svdgpu_host_free(void *p) { if (p) SVD_CUDA_CHECK(cudaFreeHost(p)); }
+
+unsigned long long svdgpu_launch_count(void) { return g_svdgpu_launches; }
 
 // ---- kernel families -------------------------------------------------------------------
 size_t svdgpu_bidiag_workspace(int m, int n, long lda) { return bidiag_workspace_bytes(m, n, lda); }

@@ -41,6 +41,8 @@ void  *svdgpu_event_create(void);
 void   svdgpu_event_destroy(void *event);
 void   svdgpu_event_record(void *event, void *stream);
 float  svdgpu_event_elapsed_ms(void *start, void *stop);   /* synchronises on stop */
+/* number of kernels this library has launched so far in this process */
+unsigned long long svdgpu_launch_count(void);
 void  *svdgpu_host_alloc(size_t bytes);         /* pinned host memory */
 void   svdgpu_host_free(void *p);
 

@@ -1,0 +1,321 @@
+"""GPU parity tests (pytest -m gpu): the CUDA path, called through the C ABI, against
+  (1) the oracle (CPU restatement of the reference) on the same seeded inputs,
+  (2) the committed golden vectors produced by the unmodified reference,
+  (3) LAPACK (numpy) for the north-star bounds  c * eps * max(m, n),
+  (4) size-independent properties at the benchmark sizes.
+
+Tolerances (written here once):
+  * bidiagonalization: overwritten A, alpha, beta within 1e-9 elementwise of the oracle on the
+    reference's own check input (uniform [1,2), srand(4)) — the criterion of bidiag_dr.c:94,166-172;
+  * singular values vs the reference: |sigma - sigma_ref| <= 1e-6 * sigma_max (the reference's own
+    error band; it is ~1e-7 * sigma_max off LAPACK);
+  * vs LAPACK: max|sigma - sigma_L| / sigma_max <= 10 eps max(m,n); Frobenius ||U^T U - I||,
+    ||V^T V - I||, ||A - U S V^T|| / ||A|| <= 100 eps max(m,n).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import util
+from util import EPS
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def D():
+    import ddc_svd_b200 as D
+    L = D.lib()
+    assert L.svdgpu_device_count() >= 1
+    return D
+
+
+def check_lapack_bounds(A, sigma, U, V, c_sig=10.0, c_vec=100.0):
+    m, n = A.shape
+    met = util.svd_metrics(A, sigma, U, V)
+    e = EPS * max(m, n)
+    assert met["ascending"], "sigma must be ascending (Calculations-Parallel.c:56)"
+    assert met["sigma_abs_over_max"] <= c_sig * e, met
+    assert met["orthU"] <= c_vec * e and met["orthV"] <= c_vec * e, met
+    assert met["resid"] <= c_vec * e, met
+    return met
+
+
+# ------------------------------------------------------------------ phase 1: bidiagonalization
+@pytest.mark.parametrize("shape", [(1, 1), (2, 2), (3, 3), (8, 8), (33, 33), (64, 64), (65, 65), (200, 200),
+                                   (513, 512), (300, 200), (200, 300), (97, 3), (3, 97), (40, 1), (1, 40),
+                                   (129, 128), (128, 129)])
+def test_bidiag_vs_oracle(D, shape):
+    m, n = shape
+    A = util.rand_matrix(m, n, 1.0, 2.0, 4)                   # bidiag_dr.c:77,92-93
+    Ao, ao, bo = util.oracle_bidiag(A)
+    Ag, ag, bg = D.bidiag_par(A)
+    assert not np.isnan(Ag).any()
+    assert np.abs(Ag - Ao).max() <= 1e-9                       # bidiag_dr.c:94 tol, elementwise
+    assert np.abs(ag - ao).max() <= 1e-9
+    if len(bo):
+        assert np.abs(bg - bo).max() <= 1e-9
+
+
+@pytest.mark.parametrize("name", ["ref_bidiag_80x80", "ref_bidiag_90x60", "ref_bidiag_60x90"])
+def test_bidiag_vs_golden_reference(D, name):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    Ag, ag, bg = D.bidiag_par(g["A"])
+    assert np.abs(Ag - g["A_mod"]).max() <= 1e-9
+    assert np.abs(ag - g["alpha"]).max() <= 1e-9 and np.abs(bg - g["beta"]).max() <= 1e-9
+
+
+@pytest.mark.parametrize("nb", [1, 7, 32, 64])
+def test_bidiag_panel_width_invariance(D, nb):
+    # the deferred-update panel width is an implementation detail: results must not depend on it
+    A = util.rand_matrix(150, 130, 1.0, 2.0, 4)
+    Ao, ao, bo = util.oracle_bidiag(A)
+    os.environ["SVD_GPU_NB"] = str(nb)
+    try:
+        Ag, ag, bg = D.bidiag_par(A)
+    finally:
+        del os.environ["SVD_GPU_NB"]
+    assert np.abs(Ag - Ao).max() <= 1e-9 and np.abs(ag - ao).max() <= 1e-9 and np.abs(bg - bo).max() <= 1e-9
+
+
+def test_bidiag_reconstruction_property(D):
+    # A = Q_L B Q_R^T with the stored reflectors: checked through the back-transform entry point
+    m, n = 260, 200
+    A = util.rand_matrix(m, n)
+    Ag, al, be = D.bidiag_par(A)
+    B = util.bidiag_dense(al, be)
+    U, V = D.backtransform(Ag, np.eye(n), np.eye(n))           # Q_L[:, :n], Q_R
+    assert np.linalg.norm(U.T @ U - np.eye(n)) < 100 * EPS * m
+    assert np.linalg.norm(V.T @ V - np.eye(n)) < 100 * EPS * m
+    assert np.linalg.norm(A - U @ B @ V.T) / np.linalg.norm(A) < 100 * EPS * m
+
+
+def test_bidiag_zero_column_is_guarded(D):
+    # the reference divides 0/0 here (SURVEY.md 8a2 "no guard for zero norm"); we define H = I
+    A = util.rand_matrix(20, 20)
+    A[:, 0] = 0.0
+    Ag, al, be = D.bidiag_par(A)
+    assert not np.isnan(Ag).any() and not np.isnan(al).any() and not np.isnan(be).any()
+    sv = np.linalg.svd(A, compute_uv=False)
+    svb = np.linalg.svd(util.bidiag_dense(al, be), compute_uv=False)
+    assert np.abs(sv - svb).max() <= 100 * EPS * 20 * sv.max()
+
+
+# ------------------------------------------------------------------ phase 2: dDC singular values
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 6, 7, 17, 64, 200, 257, 512, 1024])
+def test_ddc_values_vs_lapack_and_oracle(D, n):
+    A = util.rand_matrix(n, n)
+    _, al, be = util.oracle_bidiag(A)
+    sv = np.linalg.svd(util.bidiag_dense(al, be), compute_uv=False)[::-1]
+    sg = D.get_singular_values(al, be)
+    assert np.all(np.diff(sg) >= 0)
+    assert np.abs(sg - sv).max() <= 10 * EPS * max(n, 8) * sv.max()
+    # reference parity inside the reference's band
+    bep = np.zeros(n); bep[: n - 1] = be
+    so = np.zeros(n)
+    util.oracle().orc_ddc_values(n, util.p(al.copy()), util.p(bep), util.p(so))
+    assert np.abs(sg - so).max() <= 1e-6 * sv.max()
+
+
+def test_ddc_values_vs_golden_reference(D):
+    g = np.load(os.path.join(GOLD, "ref_ddc_257.npz"))
+    sg = D.get_singular_values(g["alpha"], g["beta"])
+    assert np.abs(sg - g["sigma"]).max() <= 1e-6 * g["sigma"].max()
+
+
+def test_ddc_rectangular_bidiagonal(D):
+    # N x (N+1): b2[N-1] != 0 — the general form of the reference's contract
+    rng = np.random.default_rng(5)
+    N = 300
+    b1 = rng.uniform(0.5, 2.0, N); b2 = rng.uniform(0.5, 2.0, N)
+    sv = np.linalg.svd(util.bidiag_dense(b1, b2, N + 1), compute_uv=False)[::-1]
+    sg = D.get_singular_values(b1, b2)
+    assert np.abs(sg - sv).max() <= 10 * EPS * N * sv.max()
+
+
+def test_ddc_deflation_and_clusters(D):
+    # glued blocks (tiny couplings -> deflation), graded entries and negative signs
+    rng = np.random.default_rng(11)
+    N = 256
+    b1 = rng.uniform(1.0, 2.0, N) * rng.choice([-1.0, 1.0], N)
+    b2 = rng.uniform(1.0, 2.0, N)
+    b2[N - 1] = 0.0
+    b2[63] = 1e-14; b2[127] = 0.0; b2[191] = 1e-9
+    b1[:32] *= 1e-3
+    sv = np.linalg.svd(util.bidiag_dense(b1, b2[: N - 1]), compute_uv=False)[::-1]
+    sg = D.get_singular_values(b1, b2)
+    assert not np.isnan(sg).any()
+    assert np.abs(sg - sv).max() <= 10 * EPS * N * sv.max()
+
+
+# ------------------------------------------------------------------ phase 3: twisted vectors
+@pytest.mark.parametrize("n", [2, 3, 8, 64, 200, 512, 1024])
+def test_twisted_vectors(D, n):
+    A = util.rand_matrix(n, n)
+    _, al, be = util.oracle_bidiag(A)
+    B = util.bidiag_dense(al, be)
+    sv = D.get_singular_values(al, be)
+    X, Y = D.singular_vectors(al, be, sv)
+    I = np.eye(n)
+    c = 100 * EPS * max(n, 8)
+    assert np.linalg.norm(X @ X.T - I) <= c and np.linalg.norm(Y @ Y.T - I) <= c
+    assert np.linalg.norm(B - Y.T @ np.diag(sv) @ X) / np.linalg.norm(B) <= c
+    assert np.allclose(np.linalg.norm(X, axis=1), 1.0, atol=1e-14)        # NormalizeVectors :106-120
+
+
+def test_twisted_vectors_vs_golden_reference(D):
+    # vectors agree with the reference's up to sign for well separated sigma (its band: 1e-6)
+    g = np.load(os.path.join(GOLD, "ref_svd_96.npz"))
+    al, be, sig = g["alpha"], g["beta"][:95], g["sigma_phase"]
+    X, Y = D.singular_vectors(al, be, sig)
+    gap = np.minimum(np.diff(sig, prepend=-np.inf), np.diff(sig, append=np.inf))
+    sep = gap > 1e-3 * sig.max()
+    assert sep.sum() > 40
+    cx = np.abs(np.sum(X * g["X"], axis=1))
+    cy = np.abs(np.sum(Y * g["Y"], axis=1))
+    assert np.all(cx[sep] >= 1 - 1e-6) and np.all(cy[sep] >= 1 - 1e-6)
+
+
+def test_twisted_rectangular(D):
+    # B is n x (n+1): vectors of length n+1 (CalcRightSingularVectors with m = n+1)
+    rng = np.random.default_rng(2)
+    n = 200
+    a = rng.uniform(0.5, 2.0, n); b = rng.uniform(0.5, 2.0, n)
+    B = util.bidiag_dense(a, b, n + 1)
+    sv = np.linalg.svd(B, compute_uv=False)[::-1]
+    X, Y = D.singular_vectors(a, b, sv, m=n + 1)
+    c = 100 * EPS * n
+    assert np.linalg.norm(X @ X.T - np.eye(n)) <= c and np.linalg.norm(Y @ Y.T - np.eye(n)) <= c
+    assert np.linalg.norm(B - Y.T @ np.diag(sv) @ X) / np.linalg.norm(B) <= c
+
+
+# ------------------------------------------------------------------ phase 4: back-transform
+@pytest.mark.parametrize("shape", [(5, 5), (64, 64), (130, 130), (200, 200), (300, 200), (200, 300), (65, 2)])
+def test_backtransform_vs_oracle(D, shape):
+    m, n = shape
+    mn = min(m, n)
+    xl = n if m >= n else m + 1
+    rng = np.random.default_rng(7)
+    A = util.rand_matrix(m, n)
+    Ao, _, _ = util.oracle_bidiag(A)
+    X = rng.standard_normal((mn, xl)); Y = rng.standard_normal((mn, mn))
+    U, V = D.backtransform(Ao, X, Y)
+    AT = np.asfortranarray(Ao.T)
+    Xc = np.ascontiguousarray(X); Yc = np.ascontiguousarray(Y)
+    for i in range(mn):
+        u = np.zeros(m); v = np.zeros(n)
+        util.oracle().orc_apply_left(m, n, i, util.p(Ao), util.p(Yc), util.p(u))
+        util.oracle().orc_apply_right(m, n, i, util.p(AT), util.p(Xc), util.p(v))
+        assert np.abs(U[:, i] - u).max() <= 1e-12 * max(1.0, np.abs(u).max())
+        assert np.abs(V[:, i] - v).max() <= 1e-12 * max(1.0, np.abs(v).max())
+
+
+def test_multU_multV_reference_signatures(D):
+    # one vector at a time, with the reference's calling convention (multV takes the transpose)
+    L = D.lib()
+    n = 40
+    g = np.load(os.path.join(GOLD, "ref_svd_48.npz"))
+    n = 48
+    A_mod = np.asfortranarray(g["A_mod"]); AT = np.asfortranarray(A_mod.T)
+    X = np.ascontiguousarray(g["X"]); Y = np.ascontiguousarray(g["Y"])
+    for i in (0, 17, 47):
+        u = np.zeros(n); v = np.zeros(n)
+        L.multU(n, n, i, util.p(A_mod), util.p(Y), util.p(u))
+        L.multV(n, n, i, util.p(AT), util.p(X), util.p(v))
+        assert np.abs(u - g["U"][:, i]).max() <= 1e-12
+        assert np.abs(v - g["V"][:, i]).max() <= 1e-12
+
+
+# ------------------------------------------------------------------ the whole path
+@pytest.mark.parametrize("shape", [(1, 1), (2, 2), (3, 3), (5, 5), (64, 64), (100, 100), (256, 256), (512, 512),
+                                   (1024, 1024), (700, 500), (500, 700), (1025, 33), (33, 1025)])
+def test_svd_gpu_vs_lapack(D, shape):
+    m, n = shape
+    A = util.rand_matrix(m, n)                                 # test-whole-svd.c recipe
+    sigma, U, V, A_mod = D.svd_gpu(A)
+    assert U.shape == (m, min(m, n)) and V.shape == (n, min(m, n))
+    check_lapack_bounds(A, sigma, U, V)
+
+
+@pytest.mark.parametrize("n", [48, 96])
+def test_svd_gpu_vs_golden_reference(D, n):
+    g = np.load(os.path.join(GOLD, f"ref_svd_{n}.npz"))
+    sigma, U, V, A_mod = D.svd_gpu(g["A"])
+    assert np.abs(A_mod - g["A_mod"]).max() <= 1e-9            # A is overwritten with the reflectors
+    assert np.abs(sigma - g["sigma"]).max() <= 1e-6 * g["sigma"].max()
+    gap = np.minimum(np.diff(g["sigma"], prepend=-np.inf), np.diff(g["sigma"], append=np.inf))
+    sep = gap > 1e-3 * g["sigma"].max()
+    cu = np.abs(np.sum(U * g["U"], axis=0)); cv = np.abs(np.sum(V * g["V"], axis=0))
+    assert np.all(cu[sep] >= 1 - 1e-6) and np.all(cv[sep] >= 1 - 1e-6)
+    # U(:,i), V(:,i) pair with sigma[i]: the sign of u_i v_i^T is fixed even if each flips
+    for i in np.nonzero(sep)[0][:10]:
+        assert np.sign(U[:, i] @ g["U"][:, i]) == np.sign(V[:, i] @ g["V"][:, i])
+
+
+def test_svd_gpu_vs_oracle_512(D):
+    # BASELINE.json configs[0]: 512 x 512, the reference's CPU-runnable case
+    A = util.rand_matrix(512, 512)
+    sigma, U, V, A_mod = D.svd_gpu(A)
+    s_o, U_o, V_o, A_o = util.oracle_svd(A)
+    assert np.abs(A_mod - A_o).max() <= 1e-9
+    assert np.abs(sigma - s_o).max() <= 1e-6 * s_o.max()
+    check_lapack_bounds(A, sigma, U, V)
+    # we are strictly more accurate than the reference on its own input
+    sv = np.linalg.svd(A, compute_uv=False)[::-1]
+    assert np.abs(sigma - sv).max() < 1e-3 * np.abs(s_o - sv).max()
+
+
+def test_svd_gpu_values_only(D):
+    A = util.rand_matrix(300, 300)
+    s1, _, _, _ = D.svd_gpu(A, vectors=False)
+    sv = np.linalg.svd(A, compute_uv=False)[::-1]
+    assert np.abs(s1 - sv).max() <= 10 * EPS * 300 * sv.max()
+
+
+def test_svd_gpu_only_first_mn_columns_written(D):
+    # svd_gpu.c:118-121: the caller hands m x m / n x n buffers, only the first min(m,n) columns change
+    m, n = 60, 40
+    A = np.array(util.rand_matrix(m, n), order="F")
+    U = np.full((m, m), 7.0, order="F"); V = np.full((n, n), 7.0, order="F"); s = np.zeros(n)
+    D.lib().svd_gpu(m, n, util.p(A), util.p(s), util.p(U), util.p(V))
+    assert np.all(U[:, n:] == 7.0)
+    assert not np.any(U[:, :n] == 7.0)
+
+
+def test_svd_gpu_repeatable(D):
+    A = util.rand_matrix(200, 200)
+    r1 = D.svd_gpu(A); r2 = D.svd_gpu(A)
+    for a, b in zip(r1, r2):
+        assert np.array_equal(a, b)                            # deterministic reductions, no atomics
+
+
+def test_svd_gpu_scaling_and_structured_inputs(D):
+    rng = np.random.default_rng(0)
+    n = 200
+    for A in (1e-150 * util.rand_matrix(n, n), 1e150 * util.rand_matrix(n, n),
+              np.diag(np.arange(1.0, n + 1)), np.triu(rng.standard_normal((n, n))),
+              rng.standard_normal((n, 3)) @ rng.standard_normal((3, n)) + 1e-8 * rng.standard_normal((n, n))):
+        sigma, U, V, _ = D.svd_gpu(A)
+        assert not (np.isnan(sigma).any() or np.isnan(U).any() or np.isnan(V).any())
+        sv = np.linalg.svd(A, compute_uv=False)[::-1]
+        assert np.abs(sigma - sv).max() <= 10 * EPS * n * sv.max()
+        assert np.linalg.norm(A - (U * sigma) @ V.T) <= 100 * EPS * n * np.linalg.norm(A)
+
+
+# ------------------------------------------------------------------ benchmark sizes: properties
+def test_svd_gpu_4096_properties(D):
+    # BASELINE.json configs[1]; LAPACK for sigma, size-independent properties for the vectors
+    n = 4096
+    A = util.rand_matrix(n, n)
+    sigma, U, V, A_mod = D.svd_gpu(A)
+    sv = np.linalg.svd(A, compute_uv=False)[::-1]
+    e = EPS * n
+    assert np.all(np.diff(sigma) >= 0)
+    assert np.abs(sigma - sv).max() / sv.max() <= 10 * e
+    assert np.linalg.norm(U.T @ U - np.eye(n)) <= 100 * e
+    assert np.linalg.norm(V.T @ V - np.eye(n)) <= 100 * e
+    assert np.linalg.norm(A - (U * sigma) @ V.T) / np.linalg.norm(A) <= 100 * e
+    # checksum of checksums: ||A||_F^2 = sum sigma^2
+    assert abs(np.sum(sigma ** 2) - np.sum(A ** 2)) <= 100 * e * np.sum(A ** 2)

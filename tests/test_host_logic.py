@@ -20,7 +20,7 @@ def _declared_symbols():
     for h in sorted(os.listdir(INC)):
         txt = open(os.path.join(INC, h)).read()
         txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-        for m in re.finditer(r"^\s*(?:const\s+)?(?:void|int|float|double|size_t|char)\s*\*?\s*\*?\s*(\w+)\s*\(", txt, re.M):
+        for m in re.finditer(r"^\s*(?:const\s+)?(?:void|int|float|double|size_t|char|unsigned long long)\s*\*?\s*\*?\s*(\w+)\s*\(", txt, re.M):
             names.add(m.group(1))
     return names
 
