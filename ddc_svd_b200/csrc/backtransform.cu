@@ -18,7 +18,7 @@
 
 namespace svdgpu {
 
-constexpr int NBW = 64;     // WY panel width
+constexpr int NBW = 128;    // WY panel width (K of the update GEMM: 128 keeps it DMMA-bound, not C-traffic-bound)
 
 // VL[r, j] = A[r, j] for r >= j (left reflector j lives in column j from the diagonal down)
 __global__ void extract_left_kernel(int m, int nL, int nLpad, const double *__restrict__ A, long lda,
@@ -56,11 +56,11 @@ extract_right_kernel(int n, int nR, int nRpad, const double *__restrict__ A, lon
 // T = (striu(G) + 1/2 I)^{-1}, one CTA per panel, thread j owns column j.
 __global__ void __launch_bounds__(NBW) wy_tinv_kernel(const double *__restrict__ G, double *__restrict__ T)
 {
-    __shared__ double R[NBW][NBW + 1];
+    extern __shared__ double Rsm[];                 // R[i][k] at Rsm[i*(NBW+1)+k]
     const double *g = G + (size_t)blockIdx.x * NBW * NBW;
     double *tcol = T + (size_t)blockIdx.x * NBW * NBW + (size_t)threadIdx.x * NBW;   // column j of T
     const int j = threadIdx.x;
-    for (int i = 0; i < NBW; ++i) R[i][j] = (i < j) ? g[i + j * NBW] : (i == j ? 0.5 : 0.0);
+    for (int i = 0; i < NBW; ++i) Rsm[i * (NBW + 1) + j] = (i < j) ? g[i + j * NBW] : (i == j ? 0.5 : 0.0);
     __syncthreads();
     // column j of the inverse of an upper-triangular matrix, bottom-up; the column is private
     // to this thread, so it can live in (L1-cached) global memory
@@ -68,7 +68,8 @@ __global__ void __launch_bounds__(NBW) wy_tinv_kernel(const double *__restrict__
     tcol[j] = 2.0;
     for (int i = j - 1; i >= 0; --i) {
         double s = 0.0;
-        for (int k = i + 1; k <= j; ++k) s += R[i][k] * tcol[k];
+        const double *Ri = Rsm + i * (NBW + 1);
+        for (int k = i + 1; k <= j; ++k) s += Ri[k] * tcol[k];
         tcol[i] = -2.0 * s;
     }
 }
@@ -124,7 +125,11 @@ void wy_apply_device(int left, int rows, int nref, const double *A, long lda, do
         g.splitk = 1;
         dgemm_dmma(g, st);
     }
-    wy_tinv_kernel<<<np, NBW, 0, st>>>(G, T);
+    {
+        const int smem = NBW * (NBW + 1) * (int)sizeof(double);
+        SVD_CUDA_CHECK(cudaFuncSetAttribute(wy_tinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        wy_tinv_kernel<<<np, NBW, smem, st>>>(G, T);
+    }
     SVD_KERNEL_CHECK();
     // VT_p = V_p T_p for all panels: (rows - p0 - ro) x NBW
     {
@@ -148,7 +153,7 @@ void wy_apply_device(int left, int rows, int nref, const double *A, long lda, do
         if (K <= 0) continue;
         const double *Vp = V + r0 + (long)p * NBW * ld;
         const double *VTp = VT + r0 + (long)p * NBW * ld;
-        int tiles = ceil_div(nc, 64);
+        int tiles = ceil_div(nc, 64) * ceil_div(NBW, 128);
         int split = 1;
         if (tiles < 2 * nsm) {
             split = (2 * nsm) / tiles;
