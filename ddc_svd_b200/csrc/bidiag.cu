@@ -185,19 +185,47 @@ __device__ __forceinline__ Refl make_refl(double x0, double nrm2)
     return f;
 }
 
+// The two "finish" kernels are elementwise in the row / column index but carry a 2k-term panel
+// correction per element.  To keep them off the critical path they are parallelised over the
+// panel index as well: a CTA is 32 elements (lanes) x FK_SLICES panel slices (warps); slice w
+// handles panel columns q = w, w+8, ... and split partials s = w, w+8, ...; the slices are
+// combined through shared memory in a fixed order (deterministic).
+constexpr int FK_SLICES = 8;
+
 // finish_y: after gemvT of step i (panel column k).
+//   blocks [0, nColBlk): 32 trailing columns each -> y_j (new Y column), r_j (row i after H)
+//   blocks [nColBlk, ..): 256 rows each -> v written in place (A[:,i]) and into the V panel
 __global__ void __launch_bounds__(256)
 finish_y_kernel(double *__restrict__ A, long lda, int i, int m, int n, int k, int nb, int do_col,
                 double *__restrict__ P, long ldp, double *__restrict__ Q, long ldq,
                 const double *__restrict__ c, double *__restrict__ rv,
                 const double *__restrict__ tmp, long ldt, int nsplit,
-                const double *__restrict__ dots, double *__restrict__ alpha)
+                const double *__restrict__ dots, double *__restrict__ alpha, int nColBlk)
 {
     __shared__ double s_vTv[NBMAX], s_xTv[NBMAX], s_rowV[NBMAX], s_rowX[NBMAX];
-    const int t = threadIdx.x;
+    __shared__ double s_red[3][FK_SLICES][32];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     const double ci = c[i];
     Refl f;
     if (do_col) f = make_refl(ci, dots[2 * nb]); else { f.snu = 0.0; f.inv = 0.0; }
+    const int R = n - i - 1, L = m - i;
+    if ((int)blockIdx.x >= nColBlk) {
+        // ---- row part: the reflector itself
+        const int idx = (blockIdx.x - nColBlk) * 256 + t;
+        if (idx == 0) alpha[i] = do_col ? -f.snu : ci;
+        if (idx < L) {
+            const int r = i + idx;
+            if (do_col) {
+                double v = (c[r] + (idx == 0 ? f.snu : 0.0)) * f.inv;
+                A[r + (long)i * lda] = v;
+                P[r + (long)k * ldp] = v;
+            } else {
+                if (idx == 0) A[r + (long)i * lda] = 0.0;     // bidiag.c:160-162 "no reflection on left"
+                P[r + (long)k * ldp] = 0.0;
+            }
+        }
+        return;
+    }
     if (t < k) {
         double pv = P[i + (long)t * ldp], px = P[i + (long)(nb + t) * ldp];
         s_rowV[t] = pv;
@@ -205,100 +233,142 @@ finish_y_kernel(double *__restrict__ A, long lda, int i, int m, int n, int k, in
         s_vTv[t] = (dots[t] + f.snu * pv) * f.inv;
         s_xTv[t] = (dots[nb + t] + f.snu * px) * f.inv;
     }
-    if (t == 0 && blockIdx.x == 0) alpha[i] = do_col ? -f.snu : ci;
     __syncthreads();
-    const double vi = (ci + f.snu) * f.inv;
-    const int idx = blockIdx.x * blockDim.x + t;
-    const int R = n - i - 1, L = m - i;
+    const int idx = blockIdx.x * 32 + lane;
+    const int j = i + 1 + idx;
+    double corr = 0.0, sub = 0.0, tt = 0.0;
     if (idx < R) {
-        const int j = i + 1 + idx;
-        const double aij = A[i + (long)j * lda];
-        double tt = 0.0;
-        if (do_col) for (int s = 0; s < nsplit; ++s) tt += tmp[(long)s * ldt + j];
-        double corr = 0.0, rr = aij;
-        for (int q = 0; q < k; ++q) {
+        if (do_col) for (int sp = w; sp < nsplit; sp += FK_SLICES) tt += tmp[(long)sp * ldt + j];
+#pragma unroll 4
+        for (int q = w; q < k; q += FK_SLICES) {
             double yk = Q[j + (long)q * ldq], uk = Q[j + (long)(nb + q) * ldq];
             corr += yk * s_vTv[q] + uk * s_xTv[q];
-            rr -= s_rowV[q] * yk + s_rowX[q] * uk;
+            sub += s_rowV[q] * yk + s_rowX[q] * uk;
         }
+    }
+    s_red[0][w][lane] = corr; s_red[1][w][lane] = sub; s_red[2][w][lane] = tt;
+    __syncthreads();
+    if (w == 0 && idx < R) {
+        corr = 0.0; sub = 0.0; tt = 0.0;
+#pragma unroll
+        for (int z = 0; z < FK_SLICES; ++z) { corr += s_red[0][z][lane]; sub += s_red[1][z][lane]; tt += s_red[2][z][lane]; }
+        const double aij = A[i + (long)j * lda];
+        const double vi = (ci + f.snu) * f.inv;
         double y = do_col ? 2.0 * ((tt + f.snu * aij) * f.inv - corr) : 0.0;
         Q[j + (long)k * ldq] = y;
-        rr -= vi * y;
-        rv[j] = rr;
-    }
-    if (idx < L) {
-        const int r = i + idx;
-        if (do_col) {
-            double v = (c[r] + (idx == 0 ? f.snu : 0.0)) * f.inv;
-            A[r + (long)i * lda] = v;
-            P[r + (long)k * ldp] = v;
-        } else {
-            if (idx == 0) A[r + (long)i * lda] = 0.0;     // bidiag.c:160-162 "no reflection on left"
-            P[r + (long)k * ldp] = 0.0;
-        }
+        rv[j] = aij - sub - vi * y;
     }
 }
 
 // finish_x: after gemvN of step i.  Also forms the next current column c' (column i+1).
+//   blocks [0, nRowBlk): 32 rows each -> x_r (new X column), c'_r
+//   blocks [nRowBlk, ..): 256 columns each -> u written in place (A[i,:]) and into the U panel
+// `dots` holds nparts partial vectors (stride dstride) that are summed here; `dots1p` (optional)
+// receives this CTA's partial [V^T c', X^T c', c'.c'] for the fused pass of the next step.
 __global__ void __launch_bounds__(256)
 finish_x_kernel(double *__restrict__ A, long lda, int i, int m, int n, int k, int nb, int do_row,
                 double *__restrict__ P, long ldp, double *__restrict__ Q, long ldq,
                 double *__restrict__ c, const double *__restrict__ rv,
                 const double *__restrict__ tmp, long ldt, int nsplit,
-                const double *__restrict__ dots, double *__restrict__ beta)
+                const double *__restrict__ dots, int nparts, int dstride,
+                double *__restrict__ beta, int nRowBlk, double *__restrict__ dots1p)
 {
     __shared__ double s_yTu[NBMAX], s_uTu[NBMAX], s_rowY[NBMAX], s_rowU[NBMAX];
-    const int t = threadIdx.x;
+    __shared__ double s_d[2 * NBMAX + 2];
+    __shared__ double s_red[3][FK_SLICES][32];
+    __shared__ double s_c[32];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     const int R = n - i - 1, Lb = m - i - 1;
+    // combine the partial dot vectors (fixed order)
+    if (t < 2 * nb + 1 && (t <= k || (t >= nb && t < nb + k) || t == 2 * nb)) {
+        double a = 0.0;
+        for (int pz = 0; pz < nparts; ++pz) a += dots[(long)pz * dstride + t];
+        s_d[t] = a;
+    }
+    __syncthreads();
     const double rf = (R > 0) ? rv[i + 1] : 0.0;
     Refl f;
-    if (do_row) f = make_refl(rf, dots[2 * nb]); else { f.snu = 0.0; f.inv = 0.0; }
+    if (do_row) f = make_refl(rf, s_d[2 * nb]); else { f.snu = 0.0; f.inv = 0.0; }
     const double ufirst = do_row ? (rf + f.snu) * f.inv : 0.0;
+    if ((int)blockIdx.x >= nRowBlk) {
+        // ---- column part: the row reflector itself
+        const int idx = (blockIdx.x - nRowBlk) * 256 + t;
+        if (idx == 0 && R > 0) {
+            beta[i] = do_row ? -f.snu : rf;
+            if (!do_row) A[i + (long)(i + 1) * lda] = 0.0;    // bidiag.c:124-128
+        }
+        if (idx < R) {
+            const int j = i + 1 + idx;
+            double u = do_row ? (rv[j] + (idx == 0 ? f.snu : 0.0)) * f.inv : 0.0;
+            if (do_row) A[i + (long)j * lda] = u;
+            Q[j + (long)(nb + k) * ldq] = u;
+        }
+        return;
+    }
     if (R > 0) {
         if (t <= k) {
             double qy = Q[(i + 1) + (long)t * ldq];
             s_rowY[t] = qy;
-            s_yTu[t] = (dots[t] + f.snu * qy) * f.inv;
+            s_yTu[t] = (s_d[t] + f.snu * qy) * f.inv;
         }
         if (t < k) {
             double qu = Q[(i + 1) + (long)(nb + t) * ldq];
             s_rowU[t] = qu;
-            s_uTu[t] = (dots[nb + t] + f.snu * qu) * f.inv;
-        }
-        if (t == 0 && blockIdx.x == 0) {
-            beta[i] = do_row ? -f.snu : rf;
-            if (!do_row) A[i + (long)(i + 1) * lda] = 0.0;    // bidiag.c:124-128
+            s_uTu[t] = (s_d[nb + t] + f.snu * qu) * f.inv;
         }
     }
     __syncthreads();
-    const int idx = blockIdx.x * blockDim.x + t;
-    if (R > 0 && idx < Lb) {
-        const int r = i + 1 + idx;
-        const double ar = A[r + (long)(i + 1) * lda];
-        double tt = 0.0;
-        if (do_row) for (int s = 0; s < nsplit; ++s) tt += tmp[(long)s * ldt + r];
-        double corr = 0.0, cc = ar;
-        for (int q = 0; q <= k; ++q) {
+    const int idx = blockIdx.x * 32 + lane;
+    const int r = i + 1 + idx;
+    const bool live = (R > 0 && idx < Lb);
+    double corr = 0.0, sub = 0.0, tt = 0.0;
+    if (live) {
+        if (do_row) for (int sp = w; sp < nsplit; sp += FK_SLICES) tt += tmp[(long)sp * ldt + r];
+#pragma unroll 4
+        for (int q = w; q <= k; q += FK_SLICES) {
             double vk = P[r + (long)q * ldp];
             corr += vk * s_yTu[q];
-            cc -= vk * s_rowY[q];
+            sub += vk * s_rowY[q];
         }
-        for (int q = 0; q < k; ++q) {
+#pragma unroll 4
+        for (int q = w; q < k; q += FK_SLICES) {
             double xk = P[r + (long)(nb + q) * ldp];
             corr += xk * s_uTu[q];
-            cc -= xk * s_rowU[q];
+            sub += xk * s_rowU[q];
         }
-        double x = do_row ? 2.0 * ((tt + f.snu * ar) * f.inv - corr) : 0.0;
-        P[r + (long)(nb + k) * ldp] = x;
-        cc -= x * ufirst;
-        c[r] = cc;
     }
-    if (idx == Lb) c[i] = 0.0;     // keeps the 128-bit loads of the next gemvT harmless
-    if (idx < R) {
-        const int j = i + 1 + idx;
-        double u = do_row ? (rv[j] + (idx == 0 ? f.snu : 0.0)) * f.inv : 0.0;
-        if (do_row) A[i + (long)j * lda] = u;
-        Q[j + (long)(nb + k) * ldq] = u;
+    s_red[0][w][lane] = corr; s_red[1][w][lane] = sub; s_red[2][w][lane] = tt;
+    __syncthreads();
+    if (w == 0) {
+        double cc = 0.0;
+        if (live) {
+            corr = 0.0; sub = 0.0; tt = 0.0;
+#pragma unroll
+            for (int z = 0; z < FK_SLICES; ++z) { corr += s_red[0][z][lane]; sub += s_red[1][z][lane]; tt += s_red[2][z][lane]; }
+            const double ar = A[r + (long)(i + 1) * lda];
+            double x = do_row ? 2.0 * ((tt + f.snu * ar) * f.inv - corr) : 0.0;
+            P[r + (long)(nb + k) * ldp] = x;
+            cc = ar - sub - x * ufirst;
+            c[r] = cc;
+        }
+        s_c[lane] = cc;
+        if (blockIdx.x == 0 && lane == 0) c[i] = 0.0;      // keeps the 128-bit loads of the next pass harmless
+    }
+    if (dots1p == nullptr) return;
+    // ---- partial panel dots of the NEW column for the fused pass of step i+1:
+    //      [0..k]: V^T c' (k+1 columns incl. the v just stored), [nb..nb+k]: X^T c', [2nb]: c'.c'
+    __syncthreads();
+    double *out = dots1p + (long)blockIdx.x * (2 * nb + 2);
+    const double cl = s_c[lane];
+    for (int q = w; q <= k; q += FK_SLICES) {
+        double pv = live ? P[r + (long)q * ldp] : 0.0;
+        double px = live ? P[r + (long)(nb + q) * ldp] : 0.0;
+        double dv = warp_sum(pv * cl), dx = warp_sum(px * cl);
+        if (lane == 0) { out[q] = dv; out[nb + q] = dx; }
+    }
+    if (w == 0) {
+        double cc2 = warp_sum(cl * cl);
+        if (lane == 0) out[2 * nb] = cc2;
     }
 }
 
@@ -433,19 +503,19 @@ void bidiag_device(int m, int n, double *A, long lda, double *alpha, double *bet
 
         if (do_col) nsplitT = launch_gemvT(A, lda, i, m, n, mpad, b, nb, k, targetT, st);
         {
-            int work = (R > m - i) ? R : (m - i);
-            finish_y_kernel<<<ceil_div(work, 256), 256, 0, st>>>(A, lda, i, m, n, k, nb, do_col, b.P, b.ldp,
-                                                                 b.Q, b.ldq, b.c, b.rv, b.tmpT, b.ldq,
-                                                                 nsplitT, b.dots1, alpha);
+            int nColBlk = ceil_div(R, 32), nRowBlk = ceil_div(m - i, 256);
+            finish_y_kernel<<<nColBlk + nRowBlk, 256, 0, st>>>(A, lda, i, m, n, k, nb, do_col, b.P, b.ldp,
+                                                               b.Q, b.ldq, b.c, b.rv, b.tmpT, b.ldq,
+                                                               nsplitT, b.dots1, alpha, nColBlk);
             SVD_KERNEL_CHECK();
         }
         if (tail && !do_row) break;             // tall/square tail: last column reflector only
         if (do_row) nsplitN = launch_gemvN(A, lda, i, m, n, mpad, b, nb, k, targetN, st);
         {
-            int work = (R > Lb + 1) ? R : (Lb + 1);
-            finish_x_kernel<<<ceil_div(work, 256), 256, 0, st>>>(A, lda, i, m, n, k, nb, do_row, b.P, b.ldp,
-                                                                 b.Q, b.ldq, b.c, b.rv, b.tmpN, lda, nsplitN,
-                                                                 b.dots2, beta);
+            int nRowBlk = Lb > 0 ? ceil_div(Lb, 32) : 1, nColBlk = ceil_div(R, 256);
+            finish_x_kernel<<<nRowBlk + nColBlk, 256, 0, st>>>(A, lda, i, m, n, k, nb, do_row, b.P, b.ldp,
+                                                               b.Q, b.ldq, b.c, b.rv, b.tmpN, lda, nsplitN,
+                                                               b.dots2, 1, 0, beta, nRowBlk, nullptr);
             SVD_KERNEL_CHECK();
         }
         ++k;

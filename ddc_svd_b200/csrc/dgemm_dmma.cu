@@ -118,6 +118,23 @@ dgemm_dmma_kernel(GemmArgs g)
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    // C -= A*B style updates (alpha = +-1, beta != 0): start the accumulators from C so that the
+    // read of the C tile overlaps the pipeline prologue instead of trailing the main loop
+    const bool cinit = (g.splitk <= 1) && (g.beta != 0.0) && (g.alpha == 1.0 || g.alpha == -1.0);
+    if (cinit) {
+        const double sc = g.beta * g.alpha;          // beta/alpha for alpha = +-1
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) {
+            const int mm = m0 + wm0 + mi * 8 + gq;
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int nn = n0 + wn0 + ni * 8 + 2 * tq + e;
+                    if (mm < M && nn < N) acc[mi][ni][e] = sc * C[mm + (long)nn * g.ldc];
+                }
+        }
+    }
 
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
@@ -157,7 +174,7 @@ dgemm_dmma_kernel(GemmArgs g)
     cp_async_wait<0>();
 
     const double alpha = g.alpha;
-    const double beta = (g.splitk > 1) ? 0.0 : g.beta;
+    const double beta = (g.splitk > 1 || cinit) ? 0.0 : g.beta;
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi) {
         const int mm = m0 + wm0 + mi * 8 + gq;
