@@ -260,39 +260,34 @@ finish_y_kernel(double *__restrict__ A, long lda, int i, int m, int n, int k, in
     }
 }
 
-// finish_x: after gemvN of step i.  Also forms the next current column c' (column i+1).
-//   blocks [0, nRowBlk): 32 rows each -> x_r (new X column), c'_r
-//   blocks [nRowBlk, ..): 256 columns each -> u written in place (A[i,:]) and into the U panel
-// `dots` holds nparts partial vectors (stride dstride) that are summed here; `dots1p` (optional)
-// receives this CTA's partial [V^T c', X^T c', c'.c'] for the fused pass of the next step.
-__global__ void __launch_bounds__(256)
+// finish_x: after the row-dot pass of step i.  Also forms the next current column c' (column i+1).
+//   blocks [0, nRowBlk): 32*RG rows each -> x_r (new X column), c'_r
+//   blocks [nRowBlk, ..): 256*RG columns each -> u written in place (A[i,:]) and into the U panel
+// With dots1p != NULL (fused path) every row block also leaves its partial [V^T c' | X^T c' | c'.c']
+// and the last row block to finish combines all partials, in a fixed order, into dots1.
+template <int RG>
+__global__ void __launch_bounds__(256 * RG)
 finish_x_kernel(double *__restrict__ A, long lda, int i, int m, int n, int k, int nb, int do_row,
                 double *__restrict__ P, long ldp, double *__restrict__ Q, long ldq,
                 double *__restrict__ c, const double *__restrict__ rv,
                 const double *__restrict__ tmp, long ldt, int nsplit,
-                const double *__restrict__ dots, int nparts, int dstride,
-                double *__restrict__ beta, int nRowBlk, double *__restrict__ dots1p)
+                const double *__restrict__ dots, double *__restrict__ beta, int nRowBlk,
+                double *__restrict__ dots1p, double *__restrict__ dots1, unsigned *__restrict__ counter)
 {
     __shared__ double s_yTu[NBMAX], s_uTu[NBMAX], s_rowY[NBMAX], s_rowU[NBMAX];
-    __shared__ double s_d[2 * NBMAX + 2];
-    __shared__ double s_red[3][FK_SLICES][32];
-    __shared__ double s_c[32];
-    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    __shared__ double s_red[RG][3][FK_SLICES][32];
+    __shared__ double s_c[RG][32];
+    __shared__ double s_dp[RG][2 * NBMAX + 2];
+    __shared__ int s_last;
+    const int t = threadIdx.x, lane = t & 31, grp = t >> 8, w = (t >> 5) & (FK_SLICES - 1);
     const int R = n - i - 1, Lb = m - i - 1;
-    // combine the partial dot vectors (fixed order)
-    if (t < 2 * nb + 1 && (t <= k || (t >= nb && t < nb + k) || t == 2 * nb)) {
-        double a = 0.0;
-        for (int pz = 0; pz < nparts; ++pz) a += dots[(long)pz * dstride + t];
-        s_d[t] = a;
-    }
-    __syncthreads();
     const double rf = (R > 0) ? rv[i + 1] : 0.0;
     Refl f;
-    if (do_row) f = make_refl(rf, s_d[2 * nb]); else { f.snu = 0.0; f.inv = 0.0; }
+    if (do_row) f = make_refl(rf, dots[2 * nb]); else { f.snu = 0.0; f.inv = 0.0; }
     const double ufirst = do_row ? (rf + f.snu) * f.inv : 0.0;
     if ((int)blockIdx.x >= nRowBlk) {
         // ---- column part: the row reflector itself
-        const int idx = (blockIdx.x - nRowBlk) * 256 + t;
+        const int idx = (blockIdx.x - nRowBlk) * (256 * RG) + t;
         if (idx == 0 && R > 0) {
             beta[i] = do_row ? -f.snu : rf;
             if (!do_row) A[i + (long)(i + 1) * lda] = 0.0;    // bidiag.c:124-128
@@ -309,16 +304,16 @@ finish_x_kernel(double *__restrict__ A, long lda, int i, int m, int n, int k, in
         if (t <= k) {
             double qy = Q[(i + 1) + (long)t * ldq];
             s_rowY[t] = qy;
-            s_yTu[t] = (s_d[t] + f.snu * qy) * f.inv;
+            s_yTu[t] = (dots[t] + f.snu * qy) * f.inv;
         }
         if (t < k) {
             double qu = Q[(i + 1) + (long)(nb + t) * ldq];
             s_rowU[t] = qu;
-            s_uTu[t] = (s_d[nb + t] + f.snu * qu) * f.inv;
+            s_uTu[t] = (dots[nb + t] + f.snu * qu) * f.inv;
         }
     }
     __syncthreads();
-    const int idx = blockIdx.x * 32 + lane;
+    const int idx = (blockIdx.x * RG + grp) * 32 + lane;
     const int r = i + 1 + idx;
     const bool live = (R > 0 && idx < Lb);
     double corr = 0.0, sub = 0.0, tt = 0.0;
@@ -337,38 +332,73 @@ finish_x_kernel(double *__restrict__ A, long lda, int i, int m, int n, int k, in
             sub += xk * s_rowU[q];
         }
     }
-    s_red[0][w][lane] = corr; s_red[1][w][lane] = sub; s_red[2][w][lane] = tt;
+    s_red[grp][0][w][lane] = corr; s_red[grp][1][w][lane] = sub; s_red[grp][2][w][lane] = tt;
     __syncthreads();
     if (w == 0) {
         double cc = 0.0;
         if (live) {
             corr = 0.0; sub = 0.0; tt = 0.0;
 #pragma unroll
-            for (int z = 0; z < FK_SLICES; ++z) { corr += s_red[0][z][lane]; sub += s_red[1][z][lane]; tt += s_red[2][z][lane]; }
+            for (int z = 0; z < FK_SLICES; ++z) {
+                corr += s_red[grp][0][z][lane]; sub += s_red[grp][1][z][lane]; tt += s_red[grp][2][z][lane];
+            }
             const double ar = A[r + (long)(i + 1) * lda];
             double x = do_row ? 2.0 * ((tt + f.snu * ar) * f.inv - corr) : 0.0;
             P[r + (long)(nb + k) * ldp] = x;
             cc = ar - sub - x * ufirst;
             c[r] = cc;
         }
-        s_c[lane] = cc;
-        if (blockIdx.x == 0 && lane == 0) c[i] = 0.0;      // keeps the 128-bit loads of the next pass harmless
+        s_c[grp][lane] = cc;
+        if (blockIdx.x == 0 && grp == 0 && lane == 0) c[i] = 0.0;   // keeps the 128-bit loads of the next pass harmless
     }
     if (dots1p == nullptr) return;
-    // ---- partial panel dots of the NEW column for the fused pass of step i+1:
+    // ---- partial panel dots of the NEW column c' for the fused pass of step i+1:
     //      [0..k]: V^T c' (k+1 columns incl. the v just stored), [nb..nb+k]: X^T c', [2nb]: c'.c'
     __syncthreads();
-    double *out = dots1p + (long)blockIdx.x * (2 * nb + 2);
-    const double cl = s_c[lane];
+    const int S1 = 2 * nb + 2;
+    const double cl = s_c[grp][lane];
     for (int q = w; q <= k; q += FK_SLICES) {
         double pv = live ? P[r + (long)q * ldp] : 0.0;
         double px = live ? P[r + (long)(nb + q) * ldp] : 0.0;
         double dv = warp_sum(pv * cl), dx = warp_sum(px * cl);
-        if (lane == 0) { out[q] = dv; out[nb + q] = dx; }
+        if (lane == 0) { s_dp[grp][q] = dv; s_dp[grp][nb + q] = dx; }
     }
     if (w == 0) {
         double cc2 = warp_sum(cl * cl);
-        if (lane == 0) out[2 * nb] = cc2;
+        if (lane == 0) s_dp[grp][2 * nb] = cc2;
+    }
+    __syncthreads();
+    const int ne = 2 * k + 3;                       // entries: [0..k], [nb..nb+k], [2nb]
+    {
+        double *out = dots1p + (long)blockIdx.x * S1;
+        for (int e = t; e < ne; e += 256 * RG) {
+            const int slot = (e <= k) ? e : (e <= 2 * k + 1 ? nb + (e - k - 1) : 2 * nb);
+            double a2 = 0.0;
+#pragma unroll
+            for (int gq = 0; gq < RG; ++gq) a2 += s_dp[gq][slot];
+            out[slot] = a2;
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (t == 0) s_last = (atomicAdd(counter, 1u) == (unsigned)(nRowBlk - 1)) ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    {
+        // 4 threads per entry, partials split in 4 contiguous ranges, combined in a fixed order
+        const int e = t >> 2, part = t & 3;
+        const int slot = (e <= k) ? e : (e <= 2 * k + 1 ? nb + (e - k - 1) : 2 * nb);
+        double sacc = 0.0;
+        if (e < ne) {
+            const int chunk = (nRowBlk + 3) / 4;
+            const int p0 = part * chunk, p1 = min(nRowBlk, p0 + chunk);
+            for (int pz = p0; pz < p1; ++pz) sacc += __ldcg(dots1p + (long)pz * S1 + slot);
+        }
+        sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+        sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+        if (e < ne && part == 0) dots1[slot] = sacc;
+        if (t == 0) *counter = 0u;
     }
 }
 
@@ -378,7 +408,14 @@ __global__ void col_init_kernel(const double *__restrict__ A, int m, long lda, d
     if (r < lda) c[r] = (r < m) ? A[r] : 0.0;
 }
 
+} // namespace svdgpu
+#include "bidiag_fused.cuh"
+namespace svdgpu {
+
 // ---------------------------------------------------------------------------------------
+constexpr int TMPN_ROWS = (BIDIAG_MAX_SPLIT > FZ_MAX_CLUSTERS) ? BIDIAG_MAX_SPLIT : FZ_MAX_CLUSTERS;
+constexpr int DOT_SLOTS = 2 * NBMAX + 2;
+
 size_t bidiag_workspace_bytes(int m, int n, long lda)
 {
     long ldq = round_up(n, 2);
@@ -388,16 +425,20 @@ size_t bidiag_workspace_bytes(int m, int n, long lda)
     d += (size_t)lda;                      // c
     d += (size_t)ldq + 2;                  // rv
     d += (size_t)BIDIAG_MAX_SPLIT * ldq;   // tmpT
-    d += (size_t)BIDIAG_MAX_SPLIT * lda;   // tmpN
-    d += 2 * (2 * NBMAX + 2);              // dots
+    d += (size_t)TMPN_ROWS * lda;          // tmpN
+    d += 2 * DOT_SLOTS;                    // dots1, dots2 (final)
+    d += (size_t)(ceil_div(m, 128) + 1) * DOT_SLOTS;   // dots1 partials (finish_x<4> row blocks)
+    d += (size_t)FZ_MAX_CLUSTERS * DOT_SLOTS;          // dots2 partials (fused pass clusters)
+    d += 8;                                // counters
     return d * sizeof(double);
 }
 
 struct BidiagBufs {
-    double *P, *Q, *c, *rv, *tmpT, *tmpN, *dots1, *dots2;
+    double *P, *Q, *c, *rv, *tmpT, *tmpN, *dots1, *dots2, *dots1p, *dots2p;
+    unsigned *counters;
     long ldp, ldq;
 };
-static BidiagBufs carve(void *workspace, int n, long lda)
+static BidiagBufs carve(void *workspace, int m, int n, long lda)
 {
     BidiagBufs b;
     b.ldp = lda; b.ldq = round_up(n, 2);
@@ -407,9 +448,12 @@ static BidiagBufs carve(void *workspace, int n, long lda)
     b.c = w;      w += (size_t)lda;
     b.rv = w;     w += (size_t)b.ldq + 2;
     b.tmpT = w;   w += (size_t)BIDIAG_MAX_SPLIT * b.ldq;
-    b.tmpN = w;   w += (size_t)BIDIAG_MAX_SPLIT * lda;
-    b.dots1 = w;  w += 2 * NBMAX + 2;
-    b.dots2 = w;
+    b.tmpN = w;   w += (size_t)TMPN_ROWS * lda;
+    b.dots1 = w;  w += DOT_SLOTS;
+    b.dots2 = w;  w += DOT_SLOTS;
+    b.dots1p = w; w += (size_t)(ceil_div(m, 128) + 1) * DOT_SLOTS;
+    b.dots2p = w; w += (size_t)FZ_MAX_CLUSTERS * DOT_SLOTS;
+    b.counters = (unsigned *)w;
     return b;
 }
 
@@ -466,12 +510,69 @@ static int launch_gemvN(const double *A, long lda, int i, int m, int n, int mpad
     return rowBlocks == 0 ? 0 : nsplit;
 }
 
-static void sm_targets(int &targetT, int &targetN)
+static int sm_targets(int &targetT, int &targetN)
 {
     int dev = 0, nsm = 148;
     SVD_CUDA_CHECK(cudaGetDevice(&dev));
     SVD_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
     targetT = nsm * 4; targetN = nsm * 8;
+    return nsm;
+}
+
+
+// ---- fused pass launch (cluster launch, TMA/mbarrier kernel of bidiag_fused.cuh) ---------------
+struct FusedPlan { bool ok; int CS, RPT, Lc, T, NC; };
+static FusedPlan plan_fused(int i, int m, int n, int mpad, int nsm, int min_rows, int min_cols)
+{
+    FusedPlan p = {false, 1, 8, 0, 0, 0};
+    const int L = m - i, R = n - i - 1;
+    if (L < min_rows || R < min_cols) return p;
+    const int Ltot = mpad - (i & ~1);
+    int CS = 1;
+    while (CS <= FZ_MAXCS && round_up(ceil_div(Ltot, CS), 2) > FZ_STAGE) CS *= 2;
+    if (CS > FZ_MAXCS) return p;
+    p.CS = CS;
+    p.Lc = (int)round_up(ceil_div(Ltot, CS), 2);
+    p.RPT = 1;
+    while (1024 * p.RPT < p.Lc) p.RPT *= 2;
+    const int cbw = 8 / p.RPT;
+    p.T = ceil_div(R, cbw);
+    int maxc = nsm / CS;
+    if (maxc > FZ_MAX_CLUSTERS) maxc = FZ_MAX_CLUSTERS;
+    p.NC = p.T < maxc ? p.T : maxc;
+    p.ok = (p.NC >= 1);
+    return p;
+}
+
+template <int RPT> static void launch_fused_t(const FusedArgs &fa, const FusedPlan &pl, cudaStream_t st)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(pl.NC * pl.CS);
+    cfg.blockDim = dim3(FZ_THREADS);
+    cfg.dynamicSmemBytes = FZ_SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = pl.CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    SVD_CUDA_CHECK(cudaLaunchKernelEx(&cfg, fused_pass_kernel<RPT>, fa));
+    SVD_KERNEL_CHECK();
+}
+static void launch_fused(const FusedArgs &fa, const FusedPlan &pl, cudaStream_t st)
+{
+    switch (pl.RPT) {
+    case 1: launch_fused_t<1>(fa, pl, st); break;
+    case 2: launch_fused_t<2>(fa, pl, st); break;
+    case 4: launch_fused_t<4>(fa, pl, st); break;
+    default: launch_fused_t<8>(fa, pl, st); break;
+    }
+}
+static void fused_set_attributes()
+{
+    SVD_CUDA_CHECK(cudaFuncSetAttribute(fused_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FZ_SMEM_BYTES));
+    SVD_CUDA_CHECK(cudaFuncSetAttribute(fused_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FZ_SMEM_BYTES));
+    SVD_CUDA_CHECK(cudaFuncSetAttribute(fused_pass_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FZ_SMEM_BYTES));
+    SVD_CUDA_CHECK(cudaFuncSetAttribute(fused_pass_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FZ_SMEM_BYTES));
 }
 
 void bidiag_device(int m, int n, double *A, long lda, double *alpha, double *beta, void *workspace,
@@ -484,12 +585,20 @@ void bidiag_device(int m, int n, double *A, long lda, double *alpha, double *bet
         fprintf(stderr, "bidiag_device: lda (%ld) must be even and >= round_up(m,2)\n", lda);
         abort();
     }
-    const BidiagBufs b = carve(workspace, n, lda);
+    const BidiagBufs b = carve(workspace, m, n, lda);
     int targetT, targetN;
-    sm_targets(targetT, targetN);
+    const int nsm = sm_targets(targetT, targetN);
+    const char *fenv = getenv("SVD_GPU_FUSED");
+    const bool use_fused = !(fenv && fenv[0] == '0');
+    if (use_fused) fused_set_attributes();
+    // thresholds below which the split passes are used (overridable for tests)
+    const char *e1 = getenv("SVD_GPU_FUSED_MIN_ROWS"), *e2 = getenv("SVD_GPU_FUSED_MIN_COLS");
+    const int fz_min_rows = e1 ? atoi(e1) : FZ_MIN_ROWS, fz_min_cols = e2 ? atoi(e2) : FZ_MIN_COLS;
+    bool dots1_ready = false;       // dots1 (final) matches the current column c
 
     SVD_CUDA_CHECK(cudaMemsetAsync(b.rv, 0, sizeof(double) * ((size_t)b.ldq + 2), st));
-    SVD_CUDA_CHECK(cudaMemsetAsync(b.dots1, 0, sizeof(double) * 2 * (2 * NBMAX + 2), st));
+    SVD_CUDA_CHECK(cudaMemsetAsync(b.dots1, 0, sizeof(double) * 2 * DOT_SLOTS, st));
+    SVD_CUDA_CHECK(cudaMemsetAsync(b.counters, 0, 8 * sizeof(double), st));
     col_init_kernel<<<ceil_div(lda, 256), 256, 0, st>>>(A, m, lda, b.c);
     SVD_KERNEL_CHECK();
 
@@ -501,6 +610,30 @@ void bidiag_device(int m, int n, double *A, long lda, double *alpha, double *bet
         const int R = n - i - 1, Lb = m - i - 1;
         int nsplitT = 0, nsplitN = 0;
 
+        FusedPlan pl = {false, 1, 8, 0, 0, 0};
+        if (use_fused && !tail && do_col && do_row) pl = plan_fused(i, m, n, mpad, nsm, fz_min_rows < 2 ? 2 : fz_min_rows, fz_min_cols < 1 ? 1 : fz_min_cols);
+        if (pl.ok) {
+            // ---- fused step: ONE read of the trailing matrix gives both A^T c and A r
+            if (!dots1_ready) {
+                // only the panel dots / norm of c (the "extra" CTAs of gemvT, no column groups)
+                gemvT_kernel<<<dim3(2 * k + 1, 1), GT_WARPS * 32, 0, st>>>(A, lda, i, m, n, mpad, b.c, b.tmpT, b.ldq,
+                                                                           0, 0, b.P, b.ldp, nb, k, b.dots1);
+                SVD_KERNEL_CHECK();
+            }
+            FusedArgs fa;
+            fa.A = A; fa.lda = lda; fa.i = i; fa.m = m; fa.n = n; fa.mpad = mpad; fa.k = k; fa.nb = nb;
+            fa.P = b.P; fa.ldp = b.ldp; fa.Q = b.Q; fa.ldq = b.ldq; fa.c = b.c; fa.rv = b.rv;
+            fa.tmpN = b.tmpN; fa.ldt = lda; fa.dots1 = b.dots1; fa.dots2p = b.dots2p; fa.dots2 = b.dots2;
+            fa.counter = b.counters; fa.alpha = alpha; fa.T = pl.T; fa.NC = pl.NC; fa.Lc = pl.Lc;
+            launch_fused(fa, pl, st);
+            const int nRowBlk = ceil_div(Lb, 128), nColBlk = ceil_div(R, 1024);
+            finish_x_kernel<4><<<nRowBlk + nColBlk, 1024, 0, st>>>(A, lda, i, m, n, k, nb, 1, b.P, b.ldp, b.Q, b.ldq,
+                                                                   b.c, b.rv, b.tmpN, lda, pl.NC, b.dots2, beta,
+                                                                   nRowBlk, b.dots1p, b.dots1, b.counters + 1);
+            SVD_KERNEL_CHECK();
+            dots1_ready = true;
+        } else {
+        dots1_ready = false;
         if (do_col) nsplitT = launch_gemvT(A, lda, i, m, n, mpad, b, nb, k, targetT, st);
         {
             int nColBlk = ceil_div(R, 32), nRowBlk = ceil_div(m - i, 256);
@@ -513,11 +646,12 @@ void bidiag_device(int m, int n, double *A, long lda, double *alpha, double *bet
         if (do_row) nsplitN = launch_gemvN(A, lda, i, m, n, mpad, b, nb, k, targetN, st);
         {
             int nRowBlk = Lb > 0 ? ceil_div(Lb, 32) : 1, nColBlk = ceil_div(R, 256);
-            finish_x_kernel<<<nRowBlk + nColBlk, 256, 0, st>>>(A, lda, i, m, n, k, nb, do_row, b.P, b.ldp,
-                                                               b.Q, b.ldq, b.c, b.rv, b.tmpN, lda, nsplitN,
-                                                               b.dots2, 1, 0, beta, nRowBlk, nullptr);
+            finish_x_kernel<1><<<nRowBlk + nColBlk, 256, 0, st>>>(A, lda, i, m, n, k, nb, do_row, b.P, b.ldp,
+                                                                  b.Q, b.ldq, b.c, b.rv, b.tmpN, lda, nsplitN,
+                                                                  b.dots2, beta, nRowBlk, nullptr, nullptr, nullptr);
             SVD_KERNEL_CHECK();
         }
+        }   // split path
         ++k;
         if (k == nb && i + 1 < mn) {
             // trailing update: A[i+1:, i+1:] -= [V|X][i+1:, :] * [Y|U][i+1:, :]^T
@@ -538,7 +672,7 @@ void bidiag_device(int m, int n, double *A, long lda, double *alpha, double *bet
 void bidiag_pass_probe(int m, int n, const double *A, long lda, void *workspace, int which, cudaStream_t st)
 {
     const int mpad = (int)round_up(m, 2);
-    const BidiagBufs b = carve(workspace, n, lda);
+    const BidiagBufs b = carve(workspace, m, n, lda);
     int targetT, targetN;
     sm_targets(targetT, targetN);
     if (which == 0) launch_gemvT(A, lda, 0, m, n, mpad, b, 32, 0, targetT, st);

@@ -80,6 +80,38 @@ def test_bidiag_panel_width_invariance(D, nb):
     assert np.abs(Ag - Ao).max() <= 1e-9 and np.abs(ag - ao).max() <= 1e-9 and np.abs(bg - bo).max() <= 1e-9
 
 
+@pytest.mark.parametrize("shape", [(1500, 1400), (4200, 300), (8704, 256), (16500, 130), (33000, 100)])
+def test_bidiag_fused_pass_vs_oracle(D, shape):
+    # tall enough for the fused single-read pass (bidiag_fused.cuh): 1 CTA per column tile up to
+    # 8192 rows, clusters of 2 / 4 / 8 CTAs (DSMEM exchange) above
+    m, n = shape
+    A = util.rand_matrix(m, n, 1.0, 2.0, 4)
+    Ao, ao, bo = util.oracle_bidiag(A)
+    Ag, ag, bg = D.bidiag_par(A)
+    assert np.abs(Ag - Ao).max() <= 1e-9 and np.abs(ag - ao).max() <= 1e-9 and np.abs(bg - bo).max() <= 1e-9
+    os.environ["SVD_GPU_FUSED"] = "0"
+    try:
+        As, a_s, b_s = D.bidiag_par(A)                         # split gemvT/gemvN passes
+    finally:
+        del os.environ["SVD_GPU_FUSED"]
+    assert np.abs(Ag - As).max() <= 1e-10 and np.abs(ag - a_s).max() <= 1e-10 * max(1.0, np.abs(ag).max())
+
+
+@pytest.mark.parametrize("shape", [(300, 200), (200, 300), (513, 512), (97, 80)])
+def test_bidiag_fused_pass_small_tiles(D, shape):
+    # force the fused pass on small trailing blocks too (all tile shapes, ragged last tiles)
+    m, n = shape
+    A = util.rand_matrix(m, n, 1.0, 2.0, 4)
+    Ao, ao, bo = util.oracle_bidiag(A)
+    os.environ["SVD_GPU_FUSED_MIN_ROWS"] = "8"; os.environ["SVD_GPU_FUSED_MIN_COLS"] = "3"
+    try:
+        Ag, ag, bg = D.bidiag_par(A)
+    finally:
+        del os.environ["SVD_GPU_FUSED_MIN_ROWS"]; del os.environ["SVD_GPU_FUSED_MIN_COLS"]
+    assert not np.isnan(Ag).any()
+    assert np.abs(Ag - Ao).max() <= 1e-9 and np.abs(ag - ao).max() <= 1e-9 and np.abs(bg - bo).max() <= 1e-9
+
+
 def test_bidiag_reconstruction_property(D):
     # A = Q_L B Q_R^T with the stored reflectors: checked through the back-transform entry point
     m, n = 260, 200
