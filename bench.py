@@ -41,19 +41,22 @@ def peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
 
 
-def bidiag_bytes(m, n, nb):
-    """Algorithmic HBM bytes of the panel bidiagonalization (DESIGN.md 'bytes per unit'):
-    per step one read of the trailing block for each of the two passes, plus one read+write of
-    the trailing block per panel for the deferred rank-2nb update.  Also returns the survey's
-    reference figure 12*S for the unblocked 3-transfer scheme."""
+def bidiag_bytes(m, n, nb, fused=True):
+    """Algorithmic HBM bytes of the panel bidiagonalization (DESIGN.md 3.1 'bytes per unit').
+    Per step: the fused pass reads the trailing block (m-i) x (n-i-1) once; the split passes read
+    it twice ((m-i)(n-i-1) for the column dots, (m-i-1)(n-i-1) for the row dots); plus one read+write
+    of the trailing block per panel for the deferred rank-2nb update.  The fused pass is used while
+    the trailing block has >= 1024 rows and >= 64 columns (bidiag.cu:plan_fused).  Also returns the
+    survey's figure 12*S for the unblocked 3-transfer scheme."""
     mn = min(m, n)
     i = np.arange(mn - 1, dtype=np.float64)
-    sl = ((m - i) * (n - i - 1)).sum()
-    ir = i[i < n - 2]
-    sr = ((m - ir - 1) * (n - ir - 1)).sum()
+    t1 = (m - i) * (n - i - 1)
+    t2 = np.where(i < n - 2, (m - i - 1) * (n - i - 1), 0.0)
+    is_fused = (m - i >= 1024) & (n - i - 1 >= 64) & (i < n - 2) if fused else np.zeros_like(i, dtype=bool)
+    reads = np.where(is_fused, t1, t1 + t2).sum()
     ends = np.arange(nb - 1, mn - 1, nb, dtype=np.float64)
     upd = ((m - ends - 1) * (n - ends - 1)).sum()
-    return 8.0 * (sl + sr) + 16.0 * upd, 12.0 * (sl + sr)
+    return 8.0 * reads + 16.0 * upd, 12.0 * (t1 + t2).sum()
 
 
 def backxf_flops(m, n):
@@ -284,7 +287,8 @@ def run_own(args):
         ph = D.last_phase_ms()
         phase = {"bidiag_ms": ph[1], "ddc_ms": ph[2], "twisted_ms": ph[3], "backtransform_ms": ph[4]}
         pk, which = peaks()
-        b_alg, b_survey = bidiag_bytes(m, n, nb)
+        fused_on = os.environ.get("SVD_GPU_FUSED", "0") != "0"
+        b_alg, b_survey = bidiag_bytes(m, n, nb, fused_on)
         ach = b_alg / (ph[1] * 1e-3) / 1e9
         # single full-size passes of the two streaming kernels, timed alone
         wbytes = L.svdgpu_bidiag_workspace(m, n, m)
@@ -304,7 +308,8 @@ def run_own(args):
                 torch.cuda.synchronize()
                 tot += p0.elapsed_time(p1)
             probe[nm + "_full_pass_gbs"] = 8.0 * m * n / (tot / reps * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "bidiag streaming passes (gemvT_kernel + gemvN_kernel)",
+        roof = {"bound": "hbm", "kernel": "bidiag streaming passes (fused_pass_kernel; gemvT/gemvN below 1024 rows)"
+                if fused_on else "bidiag streaming passes (gemvT_kernel + gemvN_kernel)", "fused_pass": fused_on,
                 "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
                 "traffic": None, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs, copy)",
                 "algorithmic_bytes": b_alg, "phase_ms": ph[1],

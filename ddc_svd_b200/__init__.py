@@ -97,6 +97,8 @@ SIGNATURES = [
     ("svdgpu_wy_apply", None, [c_int, c_int, c_int, c_void_p, c_long, c_void_p, c_long, c_int, c_void_p, c_void_p]),
     ("svdgpu_dgemm", None, [c_int, c_int, c_int, c_int, c_int, c_double, c_void_p, c_long, c_void_p, c_long,
                             c_double, c_void_p, c_long, c_void_p]),
+    ("svdgpu_scale_matrix", None, [c_int, c_int, c_void_p, c_long, c_void_p, c_void_p, c_void_p]),
+    ("svdgpu_scale_vector", None, [c_int, c_void_p, c_void_p, c_void_p]),
     ("svdgpu_bidiag_pass_probe", None, [c_int, c_int, c_void_p, c_long, c_void_p, c_int, c_void_p]),
 ]
 

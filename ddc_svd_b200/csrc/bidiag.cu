@@ -276,11 +276,28 @@ finish_x_kernel(double *__restrict__ A, long lda, int i, int m, int n, int k, in
 {
     __shared__ double s_yTu[NBMAX], s_uTu[NBMAX], s_rowY[NBMAX], s_rowU[NBMAX];
     __shared__ double s_red[RG][3][FK_SLICES][32];
-    __shared__ double s_c[RG][32];
+    __shared__ double s_c[RG][32], s_x[RG][32];
     __shared__ double s_dp[RG][2 * NBMAX + 2];
     __shared__ int s_last;
     const int t = threadIdx.x, lane = t & 31, grp = t >> 8, w = (t >> 5) & (FK_SLICES - 1);
     const int R = n - i - 1, Lb = m - i - 1;
+    // ---- issue the long-latency loads of the row part first (they do not depend on the scalars)
+    constexpr int ZV = NBMAX / FK_SLICES + 1, ZX = NBMAX / FK_SLICES;
+    const int idx = (blockIdx.x * RG + grp) * 32 + lane;
+    const int r = i + 1 + idx;
+    const bool live = ((int)blockIdx.x < nRowBlk && R > 0 && idx < Lb);
+    double vk[ZV], xk[ZX], tt = 0.0, ar = 0.0;
+#pragma unroll
+    for (int z = 0; z < ZV; ++z) { const int q = w + FK_SLICES * z; vk[z] = (live && q <= k) ? P[r + (long)q * ldp] : 0.0; }
+#pragma unroll
+    for (int z = 0; z < ZX; ++z) { const int q = w + FK_SLICES * z; xk[z] = (live && q < k) ? P[r + (long)(nb + q) * ldp] : 0.0; }
+    if (live) {
+        if (do_row) {
+#pragma unroll 4
+            for (int sp = w; sp < nsplit; sp += FK_SLICES) tt += tmp[(long)sp * ldt + r];
+        }
+        if (w == 0) ar = A[r + (long)(i + 1) * lda];
+    }
     const double rf = (R > 0) ? rv[i + 1] : 0.0;
     Refl f;
     if (do_row) f = make_refl(rf, dots[2 * nb]); else { f.snu = 0.0; f.inv = 0.0; }
@@ -313,42 +330,28 @@ finish_x_kernel(double *__restrict__ A, long lda, int i, int m, int n, int k, in
         }
     }
     __syncthreads();
-    const int idx = (blockIdx.x * RG + grp) * 32 + lane;
-    const int r = i + 1 + idx;
-    const bool live = (R > 0 && idx < Lb);
-    double corr = 0.0, sub = 0.0, tt = 0.0;
-    if (live) {
-        if (do_row) for (int sp = w; sp < nsplit; sp += FK_SLICES) tt += tmp[(long)sp * ldt + r];
-#pragma unroll 4
-        for (int q = w; q <= k; q += FK_SLICES) {
-            double vk = P[r + (long)q * ldp];
-            corr += vk * s_yTu[q];
-            sub += vk * s_rowY[q];
-        }
-#pragma unroll 4
-        for (int q = w; q < k; q += FK_SLICES) {
-            double xk = P[r + (long)(nb + q) * ldp];
-            corr += xk * s_uTu[q];
-            sub += xk * s_rowU[q];
-        }
-    }
+    double corr = 0.0, sub = 0.0;
+#pragma unroll
+    for (int z = 0; z < ZV; ++z) { const int q = w + FK_SLICES * z; if (q <= k) { corr += vk[z] * s_yTu[q]; sub += vk[z] * s_rowY[q]; } }
+#pragma unroll
+    for (int z = 0; z < ZX; ++z) { const int q = w + FK_SLICES * z; if (q < k) { corr += xk[z] * s_uTu[q]; sub += xk[z] * s_rowU[q]; } }
     s_red[grp][0][w][lane] = corr; s_red[grp][1][w][lane] = sub; s_red[grp][2][w][lane] = tt;
     __syncthreads();
     if (w == 0) {
-        double cc = 0.0;
+        double cc = 0.0, x = 0.0;
         if (live) {
             corr = 0.0; sub = 0.0; tt = 0.0;
 #pragma unroll
             for (int z = 0; z < FK_SLICES; ++z) {
                 corr += s_red[grp][0][z][lane]; sub += s_red[grp][1][z][lane]; tt += s_red[grp][2][z][lane];
             }
-            const double ar = A[r + (long)(i + 1) * lda];
-            double x = do_row ? 2.0 * ((tt + f.snu * ar) * f.inv - corr) : 0.0;
+            x = do_row ? 2.0 * ((tt + f.snu * ar) * f.inv - corr) : 0.0;
             P[r + (long)(nb + k) * ldp] = x;
             cc = ar - sub - x * ufirst;
             c[r] = cc;
         }
         s_c[grp][lane] = cc;
+        s_x[grp][lane] = x;
         if (blockIdx.x == 0 && grp == 0 && lane == 0) c[i] = 0.0;   // keeps the 128-bit loads of the next pass harmless
     }
     if (dots1p == nullptr) return;
@@ -357,11 +360,14 @@ finish_x_kernel(double *__restrict__ A, long lda, int i, int m, int n, int k, in
     __syncthreads();
     const int S1 = 2 * nb + 2;
     const double cl = s_c[grp][lane];
-    for (int q = w; q <= k; q += FK_SLICES) {
-        double pv = live ? P[r + (long)q * ldp] : 0.0;
-        double px = live ? P[r + (long)(nb + q) * ldp] : 0.0;
-        double dv = warp_sum(pv * cl), dx = warp_sum(px * cl);
-        if (lane == 0) { s_dp[grp][q] = dv; s_dp[grp][nb + q] = dx; }
+#pragma unroll
+    for (int z = 0; z < ZV; ++z) {
+        const int q = w + FK_SLICES * z;
+        if (q <= k) {                                       // warp-uniform
+            const double xv = (q < k) ? xk[z < ZX ? z : 0] : s_x[grp][lane];
+            const double dv = warp_sum(vk[z] * cl), dx = warp_sum(xv * cl);
+            if (lane == 0) { s_dp[grp][q] = dv; s_dp[grp][nb + q] = dx; }
+        }
     }
     if (w == 0) {
         double cc2 = warp_sum(cl * cl);
@@ -386,18 +392,25 @@ finish_x_kernel(double *__restrict__ A, long lda, int i, int m, int n, int k, in
     if (!s_last) return;
     __threadfence();
     {
-        // 4 threads per entry, partials split in 4 contiguous ranges, combined in a fixed order
-        const int e = t >> 2, part = t & 3;
-        const int slot = (e <= k) ? e : (e <= 2 * k + 1 ? nb + (e - k - 1) : 2 * nb);
-        double sacc = 0.0;
-        if (e < ne) {
-            const int chunk = (nRowBlk + 3) / 4;
-            const int p0 = part * chunk, p1 = min(nRowBlk, p0 + chunk);
-            for (int pz = p0; pz < p1; ++pz) sacc += __ldcg(dots1p + (long)pz * S1 + slot);
+        // TPE threads per entry, partials split in TPE contiguous ranges, combined in a fixed order
+        constexpr int TPE = (RG >= 4) ? 4 : 1;
+        const int part = t % TPE;
+        for (int e0 = 0; e0 < ne; e0 += (256 * RG) / TPE) {
+            const int e = e0 + t / TPE;
+            const int slot = (e <= k) ? e : (e <= 2 * k + 1 ? nb + (e - k - 1) : 2 * nb);
+            double sacc = 0.0;
+            if (e < ne) {
+                const int chunk = (nRowBlk + TPE - 1) / TPE;
+                const int p0 = part * chunk, p1 = min(nRowBlk, p0 + chunk);
+#pragma unroll 8
+                for (int pz = p0; pz < p1; ++pz) sacc += __ldcg(dots1p + (long)pz * S1 + slot);
+            }
+            if (TPE == 4) {
+                sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+                sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+            }
+            if (e < ne && part == 0) dots1[slot] = sacc;
         }
-        sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
-        sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
-        if (e < ne && part == 0) dots1[slot] = sacc;
         if (t == 0) *counter = 0u;
     }
 }
@@ -524,7 +537,7 @@ static int sm_targets(int &targetT, int &targetN)
 struct FusedPlan { bool ok; int CS, RPT, Lc, T, NC; };
 static FusedPlan plan_fused(int i, int m, int n, int mpad, int nsm, int min_rows, int min_cols)
 {
-    FusedPlan p = {false, 1, 8, 0, 0, 0};
+    FusedPlan p = {false, 1, 4, 0, 0, 0};
     const int L = m - i, R = n - i - 1;
     if (L < min_rows || R < min_cols) return p;
     const int Ltot = mpad - (i & ~1);
@@ -535,7 +548,7 @@ static FusedPlan plan_fused(int i, int m, int n, int mpad, int nsm, int min_rows
     p.Lc = (int)round_up(ceil_div(Ltot, CS), 2);
     p.RPT = 1;
     while (1024 * p.RPT < p.Lc) p.RPT *= 2;
-    const int cbw = 8 / p.RPT;
+    const int cbw = FZ_CBW_MAX / p.RPT;
     p.T = ceil_div(R, cbw);
     int maxc = nsm / CS;
     if (maxc > FZ_MAX_CLUSTERS) maxc = FZ_MAX_CLUSTERS;
@@ -563,8 +576,7 @@ static void launch_fused(const FusedArgs &fa, const FusedPlan &pl, cudaStream_t 
     switch (pl.RPT) {
     case 1: launch_fused_t<1>(fa, pl, st); break;
     case 2: launch_fused_t<2>(fa, pl, st); break;
-    case 4: launch_fused_t<4>(fa, pl, st); break;
-    default: launch_fused_t<8>(fa, pl, st); break;
+    default: launch_fused_t<4>(fa, pl, st); break;
     }
 }
 static void fused_set_attributes()
@@ -572,7 +584,6 @@ static void fused_set_attributes()
     SVD_CUDA_CHECK(cudaFuncSetAttribute(fused_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FZ_SMEM_BYTES));
     SVD_CUDA_CHECK(cudaFuncSetAttribute(fused_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FZ_SMEM_BYTES));
     SVD_CUDA_CHECK(cudaFuncSetAttribute(fused_pass_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FZ_SMEM_BYTES));
-    SVD_CUDA_CHECK(cudaFuncSetAttribute(fused_pass_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FZ_SMEM_BYTES));
 }
 
 void bidiag_device(int m, int n, double *A, long lda, double *alpha, double *beta, void *workspace,
@@ -588,8 +599,10 @@ void bidiag_device(int m, int n, double *A, long lda, double *alpha, double *bet
     const BidiagBufs b = carve(workspace, m, n, lda);
     int targetT, targetN;
     const int nsm = sm_targets(targetT, targetN);
+    // SVD_GPU_FUSED=1 selects the single-read fused pass (bidiag_fused.cuh); the default is decided by
+    // measurement (profiles/): the split passes unless the fused pass is faster at this size
     const char *fenv = getenv("SVD_GPU_FUSED");
-    const bool use_fused = !(fenv && fenv[0] == '0');
+    const bool use_fused = (fenv != nullptr) ? (fenv[0] != '0') : FZ_DEFAULT_ON;
     if (use_fused) fused_set_attributes();
     // thresholds below which the split passes are used (overridable for tests)
     const char *e1 = getenv("SVD_GPU_FUSED_MIN_ROWS"), *e2 = getenv("SVD_GPU_FUSED_MIN_COLS");
@@ -610,7 +623,7 @@ void bidiag_device(int m, int n, double *A, long lda, double *alpha, double *bet
         const int R = n - i - 1, Lb = m - i - 1;
         int nsplitT = 0, nsplitN = 0;
 
-        FusedPlan pl = {false, 1, 8, 0, 0, 0};
+        FusedPlan pl = {false, 1, 4, 0, 0, 0};
         if (use_fused && !tail && do_col && do_row) pl = plan_fused(i, m, n, mpad, nsm, fz_min_rows < 2 ? 2 : fz_min_rows, fz_min_cols < 1 ? 1 : fz_min_cols);
         if (pl.ok) {
             // ---- fused step: ONE read of the trailing matrix gives both A^T c and A r
@@ -626,10 +639,17 @@ void bidiag_device(int m, int n, double *A, long lda, double *alpha, double *bet
             fa.tmpN = b.tmpN; fa.ldt = lda; fa.dots1 = b.dots1; fa.dots2p = b.dots2p; fa.dots2 = b.dots2;
             fa.counter = b.counters; fa.alpha = alpha; fa.T = pl.T; fa.NC = pl.NC; fa.Lc = pl.Lc;
             launch_fused(fa, pl, st);
-            const int nRowBlk = ceil_div(Lb, 128), nColBlk = ceil_div(R, 1024);
-            finish_x_kernel<4><<<nRowBlk + nColBlk, 1024, 0, st>>>(A, lda, i, m, n, k, nb, 1, b.P, b.ldp, b.Q, b.ldq,
-                                                                   b.c, b.rv, b.tmpN, lda, pl.NC, b.dots2, beta,
-                                                                   nRowBlk, b.dots1p, b.dots1, b.counters + 1);
+            if (Lb > 2048) {
+                const int nRowBlk = ceil_div(Lb, 128), nColBlk = ceil_div(R, 1024);
+                finish_x_kernel<4><<<nRowBlk + nColBlk, 1024, 0, st>>>(A, lda, i, m, n, k, nb, 1, b.P, b.ldp, b.Q,
+                                                                       b.ldq, b.c, b.rv, b.tmpN, lda, pl.NC, b.dots2,
+                                                                       beta, nRowBlk, b.dots1p, b.dots1, b.counters + 1);
+            } else {
+                const int nRowBlk = ceil_div(Lb, 32), nColBlk = ceil_div(R, 256);
+                finish_x_kernel<1><<<nRowBlk + nColBlk, 256, 0, st>>>(A, lda, i, m, n, k, nb, 1, b.P, b.ldp, b.Q,
+                                                                      b.ldq, b.c, b.rv, b.tmpN, lda, pl.NC, b.dots2,
+                                                                      beta, nRowBlk, b.dots1p, b.dots1, b.counters + 1);
+            }
             SVD_KERNEL_CHECK();
             dots1_ready = true;
         } else {

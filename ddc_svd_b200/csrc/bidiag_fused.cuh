@@ -11,17 +11,17 @@
 //         sweep 2:  t2 += A[:,J] r_J                 (same shared-memory tile)
 //
 // This halves the HBM traffic of the split gemvT/gemvN passes.  sm_100a mapping:
-//   * the tile (<= 64 KB per stage, 3 stages) is brought in by TMA bulk copies
+//   * the tile (<= 32 KB per stage, 6 stages: two tiles being consumed, four in flight) is brought in by TMA bulk copies
 //     (cp.async.bulk ... mbarrier::complete_tx), one per column segment, issued by an elected
 //     lane of a dedicated producer warp; full/empty mbarriers form the pipeline;
-//   * the same warp is a helper: while the copies fly it gathers the tile's panel rows
-//     (Y[j,:], U[j,:]) and reduces the 2k-term corrections the consumers will need;
+//   * four helper warps (one tile in four each) gather, while the copies fly, the tile's panel
+//     rows (Y[j,:], U[j,:]) and reduce the 2k-term corrections the consumers will need;
 //   * 16 consumer warps own fixed rows (c and the t2 accumulators live in registers for the
 //     whole pass) and read the tile from shared memory twice with conflict-free 128-bit loads;
-//   * when a column is taller than one SM can hold (8192 rows per CTA) the rows are split
+//   * when a column is taller than one stage can hold (4096 rows per CTA) the rows are split
 //     over a thread-block CLUSTER of 2/4/8 CTAs; the per-column partial sums of sweep 1 are
-//     exchanged through distributed shared memory (st.shared::cluster + remote mbarrier
-//     arrive), software-pipelined one tile ahead so the exchange latency hides behind sweep 2
+//     exchanged through distributed shared memory (st.async ... mbarrier::complete_tx on the
+//     remote barrier, so receivers need no cluster-scope acquire), software-pipelined one tile ahead so the exchange latency hides behind sweep 2
 //     of the previous tile;
 //   * clusters walk the column tiles round-robin; every cluster writes its partial t2 and its
 //     partial panel dots; the last cluster to finish combines the dot partials in a fixed
@@ -30,19 +30,24 @@
 
 namespace svdgpu {
 
-constexpr int FZ_STAGE = 8192;            // doubles per shared-memory stage (64 KB)
-constexpr int FZ_STAGES = 3;
-constexpr int FZ_XR = 4;                  // ring depth of the cross-CTA exchange
+constexpr int FZ_STAGE = 4096;            // doubles per shared-memory stage (32 KB)
+constexpr int FZ_STAGES = 6;              // FZ_D+1 tiles in consumption (pipelined exchange), the rest in flight
+constexpr int FZ_CBW_MAX = 4;             // columns per tile (rows per CTA <= 1024 -> 4 columns)
+constexpr int FZ_D = 2;                   // sweep 2 runs FZ_D tiles behind sweep 1 (hides the exchange + CTA skew)
+constexpr int FZ_XR = 8;                  // ring depth of the cross-CTA exchange (>= 2*FZ_D + 2)
 constexpr int FZ_CW = 16;                 // consumer warps
 constexpr int FZ_CT = FZ_CW * 32;         // consumer threads
-constexpr int FZ_THREADS = FZ_CT + 32;    // + producer / helper warp
+constexpr int FZ_HW = 4;                  // helper warps (tile n is prepared by helper n % FZ_HW)
+constexpr int FZ_PRE = (1 + FZ_HW) * 32;  // threads before the consumers: TMA producer warp + helpers
+constexpr int FZ_THREADS = FZ_PRE + FZ_CT;
 constexpr int FZ_MAXCS = 8;               // largest cluster
 constexpr int FZ_MAX_CLUSTERS = 148;
+constexpr bool FZ_DEFAULT_ON = false;      // see profiles/: flipped when the fused pass beats the split passes
 constexpr int FZ_MIN_ROWS = 1024;         // below this trailing height the split passes are used
 constexpr int FZ_MIN_COLS = 64;
 
 constexpr size_t FZ_SMEM_DOUBLES = (size_t)FZ_STAGES * FZ_STAGE       // tiles
-                                   + (size_t)FZ_STAGES * 8 * 2 * NBMAX // panel rows of the tile columns
+                                   + (size_t)FZ_STAGES * FZ_CBW_MAX * 2 * NBMAX // panel rows of the tile columns
                                    + 3 * FZ_STAGES * 8                 // corr, g, a_ij
                                    + 2 * FZ_CW * 8                     // per-warp column sums
                                    + FZ_XR * FZ_MAXCS * 8              // exchanged column sums
@@ -113,6 +118,15 @@ __device__ __forceinline__ void fz_st_cluster(unsigned caddr, double v)
 {
     asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(caddr), "d"(v) : "memory");
 }
+// remote shared-memory store that completes a transaction on the REMOTE mbarrier: the data is
+// visible to whoever observes the barrier phase with an ordinary CTA-scope wait (no cluster-scope
+// acquire, hence no L1 invalidate on the waiting side)
+__device__ __forceinline__ void fz_st_async(unsigned caddr, double v, unsigned cbar)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(caddr),
+                 "l"(__double_as_longlong(v)), "r"(cbar)
+                 : "memory");
+}
 __device__ __forceinline__ void fz_mbar_arrive_cluster(unsigned caddr)
 {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(caddr) : "memory");
@@ -134,15 +148,15 @@ __device__ __forceinline__ void fz_consumer_bar()
     asm volatile("bar.sync 1, %0;" ::"n"(FZ_CT) : "memory");
 }
 
-// RPT = row pairs per consumer thread (rows per CTA <= 1024*RPT), CBW = 8/RPT columns per tile
+// RPT = row pairs per consumer thread (rows per CTA <= 1024*RPT <= 4096), CBW = 4/RPT columns per tile
 template <int RPT>
 __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedArgs a)
 {
-    constexpr int CBW = 8 / RPT;
+    constexpr int CBW = FZ_CBW_MAX / RPT;
     extern __shared__ __align__(128) unsigned char fz_smem[];
     double *tile = reinterpret_cast<double *>(fz_smem);
     double *qrow = tile + (size_t)FZ_STAGES * FZ_STAGE;
-    double *hcorr = qrow + FZ_STAGES * 8 * 2 * NBMAX;
+    double *hcorr = qrow + FZ_STAGES * FZ_CBW_MAX * 2 * NBMAX;
     double *hg = hcorr + FZ_STAGES * 8;
     double *haij = hg + FZ_STAGES * 8;
     double *wsum = haij + FZ_STAGES * 8;
@@ -169,12 +183,12 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
     if (len < 0) len = 0;
 
     if (tid == 0) {
-        for (int s = 0; s < FZ_STAGES; ++s) { fz_mbar_init(full + s, 1); fz_mbar_init(empty + s, FZ_CW); }
-        for (int x = 0; x < FZ_XR; ++x) fz_mbar_init(xbar + x, CS);
+        for (int s = 0; s < FZ_STAGES; ++s) { fz_mbar_init(full + s, 2); fz_mbar_init(empty + s, FZ_CW); }
+        for (int x = 0; x < FZ_XR; ++x) fz_mbar_init(xbar + x, 1);
         hn[FZ_STAGES] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (tid == 32) {
+    if (tid == FZ_PRE) {
         const double ci = a.c[i];
         Refl f = make_refl(ci, a.dots1[2 * nb]);
         s_sc[0] = f.snu; s_sc[1] = f.inv; s_sc[2] = (ci + f.snu) * f.inv;
@@ -195,35 +209,14 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
     const int ntiles = (a.T > g) ? (a.T - g + NC - 1) / NC : 0;
 
     if (warp == 0) {
-        // ======================= producer + helper warp =======================
+        // ============================ TMA producer warp ============================
         for (int nt = 0; nt < ntiles; ++nt) {
             const int s = nt % FZ_STAGES;
             fz_mbar_wait(empty + s, ((nt / FZ_STAGES) & 1) ^ 1);
-            const int j0 = i + 1 + (g + nt * NC) * CBW;
-            int ncols = a.n - j0;
-            if (ncols > CBW) ncols = CBW;
-            for (int q = 0; q < ncols; ++q) {
-                const int j = j0 + q;
-                double corr = 0.0, gg = 0.0;
-                double *qr = qrow + (size_t)(s * 8 + q) * 2 * NBMAX;
-                for (int kk = lane; kk < k; kk += 32) {
-                    const double yk = a.Q[j + (long)kk * a.ldq], uk = a.Q[j + (long)(nb + kk) * a.ldq];
-                    corr += yk * s_vTv[kk] + uk * s_xTv[kk];
-                    gg += s_rowV[kk] * yk + s_rowX[kk] * uk;
-                    qr[kk] = yk;
-                    qr[NBMAX + kk] = uk;
-                }
-                corr = warp_sum(corr);
-                gg = warp_sum(gg);
-                if (lane == 0) {
-                    hcorr[s * 8 + q] = corr;
-                    hg[s * 8 + q] = gg;
-                    haij[s * 8 + q] = a.A[i + (long)j * a.lda];
-                }
-            }
-            if (lane == 0) hn[s] = ncols;
-            __syncwarp();
             if (lane == 0) {
+                const int j0 = i + 1 + (g + nt * NC) * CBW;
+                int ncols = a.n - j0;
+                if (ncols > CBW) ncols = CBW;
                 const unsigned bytes = (unsigned)ncols * (unsigned)len * 8u;
                 if (bytes) {
                     fz_mbar_arrive_expect_tx(full + s, bytes);
@@ -235,9 +228,53 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
                 }
             }
         }
+    } else if (warp <= FZ_HW) {
+        // ============================== helper warps ==============================
+        // per tile column j: a_ij, corr_j = Y[j,:].vTv + U[j,:].xTv, g_j = rowV.Y[j,:] + rowX.U[j,:]
+        // and a copy of the panel rows for the dot partials; all loads are issued before any use
+        for (int nt = warp - 1; nt < ntiles; nt += FZ_HW) {
+            const int s = nt % FZ_STAGES;
+            const int j0 = i + 1 + (g + nt * NC) * CBW;
+            int ncols = a.n - j0;
+            if (ncols > CBW) ncols = CBW;
+            double yk[CBW][2], uk[CBW][2], aij[CBW];
+#pragma unroll
+            for (int q = 0; q < CBW; ++q) {
+                const int j = (q < ncols) ? j0 + q : j0;
+                aij[q] = (lane == 0) ? a.A[i + (long)j * a.lda] : 0.0;
+#pragma unroll
+                for (int z = 0; z < 2; ++z) {
+                    const int kk = lane + 32 * z;
+                    yk[q][z] = (kk < k) ? a.Q[j + (long)kk * a.ldq] : 0.0;
+                    uk[q][z] = (kk < k) ? a.Q[j + (long)(nb + kk) * a.ldq] : 0.0;
+                }
+            }
+            fz_mbar_wait(empty + s, ((nt / FZ_STAGES) & 1) ^ 1);     // stage (and its helper slots) free
+#pragma unroll
+            for (int q = 0; q < CBW; ++q) {
+                double corr = 0.0, gg = 0.0;
+                double *qr = qrow + (size_t)(s * FZ_CBW_MAX + q) * 2 * NBMAX;
+#pragma unroll
+                for (int z = 0; z < 2; ++z) {
+                    const int kk = lane + 32 * z;
+                    if (kk < k) {
+                        corr += yk[q][z] * s_vTv[kk] + uk[q][z] * s_xTv[kk];
+                        gg += s_rowV[kk] * yk[q][z] + s_rowX[kk] * uk[q][z];
+                        qr[kk] = yk[q][z];
+                        qr[NBMAX + kk] = uk[q][z];
+                    }
+                }
+                corr = warp_sum(corr);
+                gg = warp_sum(gg);
+                if (lane == 0) { hcorr[s * 8 + q] = corr; hg[s * 8 + q] = gg; haij[s * 8 + q] = aij[q]; }
+            }
+            if (lane == 0) hn[s] = ncols;
+            __syncwarp();
+            if (lane == 0) fz_mbar_arrive(full + s);
+        }
     } else {
         // ============================ consumer warps ============================
-        const int cw = warp - 1, ct = tid - 32;
+        const int cw = warp - 1 - FZ_HW, ct = tid - FZ_PRE;
         double2 creg[RPT], acc[RPT];
 #pragma unroll
         for (int u = 0; u < RPT; ++u) {
@@ -268,7 +305,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
         double dY[2] = {0.0, 0.0}, dU[2] = {0.0, 0.0}, rr2 = 0.0, yr = 0.0;
         const bool colwarp = (cw == 0);
 
-        for (int nt = 0; nt <= ntiles; ++nt) {
+        for (int nt = 0; nt < ntiles + FZ_D; ++nt) {
             if (nt < ntiles) {
                 // ---- part A of tile nt: sweep 1 (column dots with c) and the cluster exchange
                 const int s = nt % FZ_STAGES;
@@ -298,26 +335,37 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
                 fz_consumer_bar();
                 if (colwarp) {
                     const int xs = nt % FZ_XR;
-                    double tot = 0.0;
-                    const int q = lane & 7;
-                    for (int w2 = 0; w2 < FZ_CW; ++w2) tot += wsum[((nt & 1) * FZ_CW + w2) * 8 + q];
-                    // lane rk ships all column sums to CTA rk of the cluster, then signals it
-                    double vals[8];
+                    // fixed-shape shuffle tree over the 16 per-warp partials of every column
+                    double vals[CBW];
 #pragma unroll
-                    for (int qq = 0; qq < 8; ++qq) vals[qq] = __shfl_sync(0xffffffffu, tot, qq);
-                    if (lane < (int)CS) {
-                        const unsigned base = fz_mapa(fz_smem_u32(xsum + (xs * FZ_MAXCS + (int)crank) * 8), (unsigned)lane);
+                    for (int qq = 0; qq < CBW; ++qq) {
+                        double v = (lane < FZ_CW) ? wsum[((nt & 1) * FZ_CW + lane) * 8 + qq] : 0.0;
+                        vals[qq] = warp_sum(v);
+                    }
+                    if (CS == 1) {
+                        if (lane == 0) {
 #pragma unroll
-                        for (int qq = 0; qq < CBW; ++qq) fz_st_cluster(base + 8u * qq, vals[qq]);
-                        fz_mbar_arrive_cluster(fz_mapa(fz_smem_u32(xbar + xs), (unsigned)lane));
+                            for (int qq = 0; qq < CBW; ++qq) xsum[(xs * FZ_MAXCS) * 8 + qq] = vals[qq];
+                        }
+                        __syncwarp();
+                        if (lane == 0) fz_mbar_arrive(xbar + xs);
+                    } else {
+                        // every CTA of the cluster receives CBW sums from each of the CS CTAs
+                        if (lane == 0) fz_mbar_arrive_expect_tx(xbar + xs, CS * CBW * 8u);
+                        if (lane < (int)CS) {
+                            const unsigned base = fz_mapa(fz_smem_u32(xsum + (xs * FZ_MAXCS + (int)crank) * 8), (unsigned)lane);
+                            const unsigned rbar = fz_mapa(fz_smem_u32(xbar + xs), (unsigned)lane);
+#pragma unroll
+                            for (int qq = 0; qq < CBW; ++qq) fz_st_async(base + 8u * qq, vals[qq], rbar);
+                        }
                     }
                 }
             }
-            if (nt > 0) {
-                // ---- part B of tile nt-1: y, r per column, sweep 2 (row dots with r)
-                const int pt = nt - 1;
+            if (nt >= FZ_D) {
+                // ---- part B of tile nt-FZ_D: y, r per column, sweep 2 (row dots with r)
+                const int pt = nt - FZ_D;
                 const int s = pt % FZ_STAGES, xs = pt % FZ_XR;
-                fz_mbar_wait_cluster(xbar + xs, (pt / FZ_XR) & 1);
+                fz_mbar_wait(xbar + xs, (pt / FZ_XR) & 1);
                 const int ncols = hn[s];
                 const double *tl = tile + (size_t)s * FZ_STAGE;
                 const int j0 = i + 1 + (g + pt * NC) * CBW;
@@ -343,7 +391,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
                                 a.Q[(j0 + q) + (long)k * a.ldq] = y;
                                 a.rv[j0 + q] = r;
                             }
-                            const double *qr = qrow + (size_t)(s * 8 + q) * 2 * NBMAX;
+                            const double *qr = qrow + (size_t)(s * FZ_CBW_MAX + q) * 2 * NBMAX;
 #pragma unroll
                             for (int z = 0; z < 2; ++z) {
                                 const int kk = lane + 32 * z;

@@ -11,6 +11,10 @@
 #include "backtransform.cuh"
 #include "../../include/cuda-helper.h"
 
+namespace svdgpu {
+void scale_matrix_device(int m, int n, double *A, long lda, double *sc, double *work, cudaStream_t st);
+void scale_vector_device(int n, double *x, const double *factor, cudaStream_t st);
+}
 using namespace svdgpu;
 unsigned long long g_svdgpu_launches = 0;
 static inline cudaStream_t S(void *s) { return (cudaStream_t)s; }
@@ -152,6 +156,14 @@ void svdgpu_dgemm(int transA, int transB, int M, int N, int K, double alpha, con
     g.B = dB; g.ldb = ldb; g.transB = transB;
     g.C = dC; g.ldc = ldc; g.alpha = alpha; g.beta = beta; g.batch = 1; g.splitk = 1;
     dgemm_dmma(g, S(stream));
+}
+void svdgpu_scale_matrix(int m, int n, double *dA, long lda, double *dscale, double *dwork, void *stream)
+{
+    scale_matrix_device(m, n, dA, lda, dscale, dwork, S(stream));
+}
+void svdgpu_scale_vector(int n, double *dx, const double *dfactor, void *stream)
+{
+    scale_vector_device(n, dx, dfactor, S(stream));
 }
 void svdgpu_bidiag_pass_probe(int m, int n, const double *dA, long lda, void *dwork, int which,
                               void *stream)

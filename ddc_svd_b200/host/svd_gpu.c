@@ -141,9 +141,12 @@ static void svd_dev_inner(int m, int n, double *dA, long lda, double *dsigma, do
     double *dalpha = (double *)scratch;             scratch += up256(sizeof(double) * (size_t)mn);
     double *dbeta = (double *)scratch;              scratch += up256(sizeof(double) * ((size_t)mn + 1));
     double *dsig = (double *)scratch;               scratch += up256(sizeof(double) * (size_t)mn);
+    double *dscale = (double *)scratch;             scratch += 256;
     void *work = scratch;
 
     svdgpu_event_record(g.ev[0], stream);
+    /* range guard: exact power-of-two scaling when max|A| is far from 1 (sigma is scaled back below) */
+    svdgpu_scale_matrix(m, n, dA, lda, dscale, (double *)work, stream);
     svdgpu_memset(dbeta, 0, sizeof(double) * ((size_t)mn + 1), stream);
     svdgpu_bidiag(m, n, dA, lda, dalpha, dbeta, work, g.nb, stream);
     svdgpu_event_record(g.ev[1], stream);
@@ -155,13 +158,14 @@ static void svd_dev_inner(int m, int n, double *dA, long lda, double *dsigma, do
     } else {
         svdgpu_event_record(g.ev[3], stream);
     }
+    svdgpu_scale_vector(mn, dsigma, dscale + 1, stream);
     svdgpu_event_record(g.ev[4], stream);
     g.ms_pending = 1;
 }
 
 static size_t small_bytes(int mn)
 {
-    return 2 * up256(sizeof(double) * (size_t)mn) + up256(sizeof(double) * ((size_t)mn + 1));
+    return 2 * up256(sizeof(double) * (size_t)mn) + up256(sizeof(double) * ((size_t)mn + 1)) + 256;
 }
 
 void svd_gpu_dev(int m, int n, double *dA, long lda, double *dsigma, double *dU, long ldu, double *dV, long ldv,

@@ -72,6 +72,12 @@ void   svdgpu_wy_apply(int left, int rows, int nref, const double *dA_mod, long 
 void   svdgpu_dgemm(int transA, int transB, int M, int N, int K, double alpha, const double *dA,
                     long lda, const double *dB, long ldb, double beta, double *dC, long ldc,
                     void *stream);
+/* power-of-two range guard (no counterpart in the reference, which overflows/underflows on inputs
+ * near 1e+-150): dscale[0] <- factor applied to dA in place (1.0 unless max|A| is outside
+ * [1e-100, 1e100]), dscale[1] <- its inverse; dwork needs 1024 doubles.  svdgpu_scale_vector
+ * multiplies dx[0..n) by *dfactor (used to scale sigma back). */
+void   svdgpu_scale_matrix(int m, int n, double *dA, long lda, double *dscale, double *dwork, void *stream);
+void   svdgpu_scale_vector(int n, double *dx, const double *dfactor, void *stream);
 /* one gemvT + one gemvN pass over the full m x n matrix (the two streaming kernels of the
  * bidiagonalization), for roofline measurement; returns nothing, only enqueues. */
 void   svdgpu_bidiag_pass_probe(int m, int n, const double *dA, long lda, void *dwork, int which,

@@ -87,7 +87,11 @@ def test_bidiag_fused_pass_vs_oracle(D, shape):
     m, n = shape
     A = util.rand_matrix(m, n, 1.0, 2.0, 4)
     Ao, ao, bo = util.oracle_bidiag(A)
-    Ag, ag, bg = D.bidiag_par(A)
+    os.environ["SVD_GPU_FUSED"] = "1"
+    try:
+        Ag, ag, bg = D.bidiag_par(A)                           # fused single-read pass
+    finally:
+        del os.environ["SVD_GPU_FUSED"]
     assert np.abs(Ag - Ao).max() <= 1e-9 and np.abs(ag - ao).max() <= 1e-9 and np.abs(bg - bo).max() <= 1e-9
     os.environ["SVD_GPU_FUSED"] = "0"
     try:
@@ -104,10 +108,11 @@ def test_bidiag_fused_pass_small_tiles(D, shape):
     A = util.rand_matrix(m, n, 1.0, 2.0, 4)
     Ao, ao, bo = util.oracle_bidiag(A)
     os.environ["SVD_GPU_FUSED_MIN_ROWS"] = "8"; os.environ["SVD_GPU_FUSED_MIN_COLS"] = "3"
+    os.environ["SVD_GPU_FUSED"] = "1"
     try:
         Ag, ag, bg = D.bidiag_par(A)
     finally:
-        del os.environ["SVD_GPU_FUSED_MIN_ROWS"]; del os.environ["SVD_GPU_FUSED_MIN_COLS"]
+        del os.environ["SVD_GPU_FUSED_MIN_ROWS"]; del os.environ["SVD_GPU_FUSED_MIN_COLS"]; del os.environ["SVD_GPU_FUSED"]
     assert not np.isnan(Ag).any()
     assert np.abs(Ag - Ao).max() <= 1e-9 and np.abs(ag - ao).max() <= 1e-9 and np.abs(bg - bo).max() <= 1e-9
 
