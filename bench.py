@@ -287,7 +287,7 @@ def run_own(args):
         ph = D.last_phase_ms()
         phase = {"bidiag_ms": ph[1], "ddc_ms": ph[2], "twisted_ms": ph[3], "backtransform_ms": ph[4]}
         pk, which = peaks()
-        fused_on = os.environ.get("SVD_GPU_FUSED", "0") != "0"
+        fused_on = os.environ.get("SVD_GPU_FUSED", "1") != "0"
         b_alg, b_survey = bidiag_bytes(m, n, nb, fused_on)
         ach = b_alg / (ph[1] * 1e-3) / 1e9
         # single full-size passes of the two streaming kernels, timed alone

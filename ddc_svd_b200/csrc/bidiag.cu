@@ -546,9 +546,9 @@ static FusedPlan plan_fused(int i, int m, int n, int mpad, int nsm, int min_rows
     if (CS > FZ_MAXCS) return p;
     p.CS = CS;
     p.Lc = (int)round_up(ceil_div(Ltot, CS), 2);
-    p.RPT = 1;
-    while (1024 * p.RPT < p.Lc) p.RPT *= 2;
-    const int cbw = FZ_CBW_MAX / p.RPT;
+    p.RPT = 2;                                   // row pairs per sweep thread: rows per CTA <= 512*RPT
+    while (512 * p.RPT < p.Lc) p.RPT *= 2;
+    const int cbw = 8 / p.RPT;
     p.T = ceil_div(R, cbw);
     int maxc = nsm / CS;
     if (maxc > FZ_MAX_CLUSTERS) maxc = FZ_MAX_CLUSTERS;
@@ -574,16 +574,16 @@ template <int RPT> static void launch_fused_t(const FusedArgs &fa, const FusedPl
 static void launch_fused(const FusedArgs &fa, const FusedPlan &pl, cudaStream_t st)
 {
     switch (pl.RPT) {
-    case 1: launch_fused_t<1>(fa, pl, st); break;
     case 2: launch_fused_t<2>(fa, pl, st); break;
-    default: launch_fused_t<4>(fa, pl, st); break;
+    case 4: launch_fused_t<4>(fa, pl, st); break;
+    default: launch_fused_t<8>(fa, pl, st); break;
     }
 }
 static void fused_set_attributes()
 {
-    SVD_CUDA_CHECK(cudaFuncSetAttribute(fused_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FZ_SMEM_BYTES));
-    SVD_CUDA_CHECK(cudaFuncSetAttribute(fused_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FZ_SMEM_BYTES));
     SVD_CUDA_CHECK(cudaFuncSetAttribute(fused_pass_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FZ_SMEM_BYTES));
+    SVD_CUDA_CHECK(cudaFuncSetAttribute(fused_pass_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FZ_SMEM_BYTES));
+    SVD_CUDA_CHECK(cudaFuncSetAttribute(fused_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FZ_SMEM_BYTES));
 }
 
 void bidiag_device(int m, int n, double *A, long lda, double *alpha, double *beta, void *workspace,

@@ -14,15 +14,17 @@
 //   * the tile (<= 32 KB per stage, 6 stages: two tiles being consumed, four in flight) is brought in by TMA bulk copies
 //     (cp.async.bulk ... mbarrier::complete_tx), one per column segment, issued by an elected
 //     lane of a dedicated producer warp; full/empty mbarriers form the pipeline;
-//   * four helper warps (one tile in four each) gather, while the copies fly, the tile's panel
-//     rows (Y[j,:], U[j,:]) and reduce the 2k-term corrections the consumers will need;
-//   * 16 consumer warps own fixed rows (c and the t2 accumulators live in registers for the
-//     whole pass) and read the tile from shared memory twice with conflict-free 128-bit loads;
+//   * helper warps gather, while the copies fly, the tile's panel rows (Y[j,:], U[j,:]) and reduce
+//     the 2k-term corrections that y_j / r_j need;
+//   * the two sweeps are done by DIFFERENT warps connected only by mbarriers (no CTA-wide barrier
+//     in the loop): 8 sweep-1 warps (c in registers) hand their column sums to a reducer warp, a
+//     finisher warp turns the cluster-wide sums into y_j, r_j, 8 sweep-2 warps (t2 accumulators in
+//     registers) consume r_j and release the stage.  Every warp runs ahead on its own, so several
+//     tiles are in different phases at once, which is what hides the per-tile latency chain;
 //   * when a column is taller than one stage can hold (4096 rows per CTA) the rows are split
 //     over a thread-block CLUSTER of 2/4/8 CTAs; the per-column partial sums of sweep 1 are
 //     exchanged through distributed shared memory (st.async ... mbarrier::complete_tx on the
-//     remote barrier, so receivers need no cluster-scope acquire), software-pipelined one tile ahead so the exchange latency hides behind sweep 2
-//     of the previous tile;
+//     remote barrier, so receivers need no cluster-scope acquire);
 //   * clusters walk the column tiles round-robin; every cluster writes its partial t2 and its
 //     partial panel dots; the last cluster to finish combines the dot partials in a fixed
 //     order (deterministic, no floating-point atomics).
@@ -31,28 +33,33 @@
 namespace svdgpu {
 
 constexpr int FZ_STAGE = 4096;            // doubles per shared-memory stage (32 KB)
-constexpr int FZ_STAGES = 6;              // FZ_D+1 tiles in consumption (pipelined exchange), the rest in flight
+constexpr int FZ_STAGES = 6;
 constexpr int FZ_CBW_MAX = 4;             // columns per tile (rows per CTA <= 1024 -> 4 columns)
-constexpr int FZ_D = 2;                   // sweep 2 runs FZ_D tiles behind sweep 1 (hides the exchange + CTA skew)
-constexpr int FZ_XR = 8;                  // ring depth of the cross-CTA exchange (>= 2*FZ_D + 2)
-constexpr int FZ_CW = 16;                 // consumer warps
-constexpr int FZ_CT = FZ_CW * 32;         // consumer threads
-constexpr int FZ_HW = 4;                  // helper warps (tile n is prepared by helper n % FZ_HW)
-constexpr int FZ_PRE = (1 + FZ_HW) * 32;  // threads before the consumers: TMA producer warp + helpers
-constexpr int FZ_THREADS = FZ_PRE + FZ_CT;
+constexpr int FZ_XR = 16;                 // ring depth of the cross-CTA exchange (>= 2*FZ_STAGES)
+constexpr int FZ_HW = 2;                  // helper warps (tile n is prepared by helper n % FZ_HW)
+constexpr int FZ_GW = 8;                  // warps per sweep group
+constexpr int FZ_GT = FZ_GW * 32;         // threads per sweep group
+// warp roles: 0 TMA producer | 1..HW helpers | HW+1 reducer | HW+2 finisher |
+//             GW sweep-1 warps | GW sweep-2 warps
+constexpr int FZ_W_RED = 1 + FZ_HW;
+constexpr int FZ_W_FIN = 2 + FZ_HW;
+constexpr int FZ_W_S1 = 3 + FZ_HW;
+constexpr int FZ_W_S2 = FZ_W_S1 + FZ_GW;
+constexpr int FZ_WARPS = FZ_W_S2 + FZ_GW;
+constexpr int FZ_THREADS = FZ_WARPS * 32;
 constexpr int FZ_MAXCS = 8;               // largest cluster
 constexpr int FZ_MAX_CLUSTERS = 148;
-constexpr bool FZ_DEFAULT_ON = false;      // see profiles/: flipped when the fused pass beats the split passes
+constexpr bool FZ_DEFAULT_ON = true;      // measured faster than the split passes at 4096^2 and 16384^2 (profiles/)
 constexpr int FZ_MIN_ROWS = 1024;         // below this trailing height the split passes are used
 constexpr int FZ_MIN_COLS = 64;
 
-constexpr size_t FZ_SMEM_DOUBLES = (size_t)FZ_STAGES * FZ_STAGE       // tiles
-                                   + (size_t)FZ_STAGES * FZ_CBW_MAX * 2 * NBMAX // panel rows of the tile columns
-                                   + 3 * FZ_STAGES * 8                 // corr, g, a_ij
-                                   + 2 * FZ_CW * 8                     // per-warp column sums
-                                   + FZ_XR * FZ_MAXCS * 8              // exchanged column sums
-                                   + 4 * NBMAX + 8;                    // vTv, xTv, rowV, rowX, scalars
-constexpr size_t FZ_SMEM_BYTES = FZ_SMEM_DOUBLES * 8 + (2 * FZ_STAGES + FZ_XR) * 8 + 8 * sizeof(int) + 128;
+constexpr size_t FZ_SMEM_DOUBLES = (size_t)FZ_STAGES * FZ_STAGE                      // tiles
+                                   + (size_t)FZ_STAGES * FZ_CBW_MAX * 2 * NBMAX      // panel rows of the tile columns
+                                   + 5 * FZ_STAGES * FZ_CBW_MAX                      // corr, g, a_ij, y, r
+                                   + FZ_STAGES * FZ_GW * FZ_CBW_MAX                  // per-warp column sums
+                                   + FZ_XR * FZ_MAXCS * FZ_CBW_MAX                   // exchanged column sums
+                                   + 4 * NBMAX + 8;                                  // vTv, xTv, rowV, rowX, scalars
+constexpr size_t FZ_SMEM_BYTES = FZ_SMEM_DOUBLES * 8 + (4 * FZ_STAGES + FZ_XR) * 8 + 16 * sizeof(int) + 128;
 
 struct FusedArgs {
     double *A; long lda;          // trailing matrix (read) and column i (the reflector is written in place)
@@ -95,6 +102,17 @@ __device__ __forceinline__ void fz_mbar_wait(uint64_t *bar, unsigned parity)
         "bra FZ_WAIT_%=;\n"
         "FZ_DONE_%=:\n"
         "}\n" ::"r"(fz_smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ bool fz_mbar_test(uint64_t *bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(fz_smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
 }
 __device__ __forceinline__ void fz_mbar_wait_cluster(uint64_t *bar, unsigned parity)
 {
@@ -143,32 +161,32 @@ __device__ __forceinline__ void fz_cluster_sync()
     asm volatile("barrier.cluster.arrive.release.aligned;\n"
                  "barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
-__device__ __forceinline__ void fz_consumer_bar()
-{
-    asm volatile("bar.sync 1, %0;" ::"n"(FZ_CT) : "memory");
-}
 
-// RPT = row pairs per consumer thread (rows per CTA <= 1024*RPT <= 4096), CBW = 4/RPT columns per tile
+// RPT = row pairs per sweep thread (rows per CTA <= 512*RPT <= 4096), CBW = 8/RPT columns per tile
 template <int RPT>
 __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedArgs a)
 {
-    constexpr int CBW = FZ_CBW_MAX / RPT;
+    constexpr int CBW = 8 / RPT;
     extern __shared__ __align__(128) unsigned char fz_smem[];
     double *tile = reinterpret_cast<double *>(fz_smem);
     double *qrow = tile + (size_t)FZ_STAGES * FZ_STAGE;
     double *hcorr = qrow + FZ_STAGES * FZ_CBW_MAX * 2 * NBMAX;
-    double *hg = hcorr + FZ_STAGES * 8;
-    double *haij = hg + FZ_STAGES * 8;
-    double *wsum = haij + FZ_STAGES * 8;
-    double *xsum = wsum + 2 * FZ_CW * 8;
-    double *s_vTv = xsum + FZ_XR * FZ_MAXCS * 8;
+    double *hg = hcorr + FZ_STAGES * FZ_CBW_MAX;
+    double *haij = hg + FZ_STAGES * FZ_CBW_MAX;
+    double *yq = haij + FZ_STAGES * FZ_CBW_MAX;
+    double *rq = yq + FZ_STAGES * FZ_CBW_MAX;
+    double *wsum = rq + FZ_STAGES * FZ_CBW_MAX;                      // [stage][warp in group][q]
+    double *xsum = wsum + FZ_STAGES * FZ_GW * FZ_CBW_MAX;            // [ring][rank][q]
+    double *s_vTv = xsum + FZ_XR * FZ_MAXCS * FZ_CBW_MAX;
     double *s_xTv = s_vTv + NBMAX;
     double *s_rowV = s_xTv + NBMAX;
     double *s_rowX = s_rowV + NBMAX;
     double *s_sc = s_rowX + NBMAX;
     uint64_t *full = reinterpret_cast<uint64_t *>(s_sc + 8);
     uint64_t *empty = full + FZ_STAGES;
-    uint64_t *xbar = empty + FZ_STAGES;
+    uint64_t *wbar = empty + FZ_STAGES;
+    uint64_t *rbar = wbar + FZ_STAGES;
+    uint64_t *xbar = rbar + FZ_STAGES;
     int *hn = reinterpret_cast<int *>(xbar + FZ_XR);       // [FZ_STAGES] column counts, [FZ_STAGES] = last flag
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -183,12 +201,17 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
     if (len < 0) len = 0;
 
     if (tid == 0) {
-        for (int s = 0; s < FZ_STAGES; ++s) { fz_mbar_init(full + s, 2); fz_mbar_init(empty + s, FZ_CW); }
+        for (int s = 0; s < FZ_STAGES; ++s) {
+            fz_mbar_init(full + s, 2);          // TMA transaction arrive + helper
+            fz_mbar_init(empty + s, FZ_GW);     // the sweep-2 warps of the tile's group
+            fz_mbar_init(wbar + s, FZ_GW);      // the sweep-1 warps of the tile's group
+            fz_mbar_init(rbar + s, 1);          // finisher
+        }
         for (int x = 0; x < FZ_XR; ++x) fz_mbar_init(xbar + x, 1);
         hn[FZ_STAGES] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (tid == FZ_PRE) {
+    if (tid == 32) {
         const double ci = a.c[i];
         Refl f = make_refl(ci, a.dots1[2 * nb]);
         s_sc[0] = f.snu; s_sc[1] = f.inv; s_sc[2] = (ci + f.snu) * f.inv;
@@ -204,9 +227,10 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
         s_xTv[tid] = (a.dots1[nb + tid] + snu * px) * inv;
     }
     __syncthreads();
-    fz_cluster_sync();                                     // barriers exist everywhere before remote arrives
+    if (CS > 1) fz_cluster_sync();                         // barriers exist everywhere before remote traffic
 
     const int ntiles = (a.T > g) ? (a.T - g + NC - 1) / NC : 0;
+    const int S2 = 2 * nb + 2;
 
     if (warp == 0) {
         // ============================ TMA producer warp ============================
@@ -266,27 +290,120 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
                 }
                 corr = warp_sum(corr);
                 gg = warp_sum(gg);
-                if (lane == 0) { hcorr[s * 8 + q] = corr; hg[s * 8 + q] = gg; haij[s * 8 + q] = aij[q]; }
+                if (lane == 0) {
+                    hcorr[s * FZ_CBW_MAX + q] = corr; hg[s * FZ_CBW_MAX + q] = gg; haij[s * FZ_CBW_MAX + q] = aij[q];
+                }
             }
             if (lane == 0) hn[s] = ncols;
             __syncwarp();
             if (lane == 0) fz_mbar_arrive(full + s);
         }
-    } else {
-        // ============================ consumer warps ============================
-        const int cw = warp - 1 - FZ_HW, ct = tid - FZ_PRE;
-        double2 creg[RPT], acc[RPT];
+    } else if (warp == FZ_W_RED) {
+        // ============================== reducer warp ==============================
+        // combines the sweep-1 warps' column sums of a tile and ships them to every CTA of the cluster
+        for (int nt = 0; nt < ntiles; ++nt) {
+            const int s = nt % FZ_STAGES, xs = nt % FZ_XR;
+            fz_mbar_wait(wbar + s, (nt / FZ_STAGES) & 1);
+            double vals[CBW];
+#pragma unroll
+            for (int qq = 0; qq < CBW; ++qq) {
+                double v = (lane < FZ_GW) ? wsum[(s * FZ_GW + lane) * FZ_CBW_MAX + qq] : 0.0;
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                v += __shfl_xor_sync(0xffffffffu, v, 4);
+                vals[qq] = __shfl_sync(0xffffffffu, v, 0);
+            }
+            if (CS == 1) {
+                if (lane == 0) {
+#pragma unroll
+                    for (int qq = 0; qq < CBW; ++qq) xsum[(xs * FZ_MAXCS) * FZ_CBW_MAX + qq] = vals[qq];
+                    fz_mbar_arrive(xbar + xs);
+                }
+            } else {
+                if (lane == 0) fz_mbar_arrive_expect_tx(xbar + xs, CS * CBW * 8u);
+                if (lane < (int)CS) {
+                    const unsigned base =
+                        fz_mapa(fz_smem_u32(xsum + (xs * FZ_MAXCS + (int)crank) * FZ_CBW_MAX), (unsigned)lane);
+                    const unsigned rb = fz_mapa(fz_smem_u32(xbar + xs), (unsigned)lane);
+#pragma unroll
+                    for (int qq = 0; qq < CBW; ++qq) fz_st_async(base + 8u * qq, vals[qq], rb);
+                }
+            }
+        }
+    } else if (warp == FZ_W_FIN) {
+        // ============================== finisher warp ==============================
+        // y_j, r_j of every tile column once the cluster-wide column sums are in; rank 0 also stores
+        // them (new Y column, row vector r) and accumulates the panel dots Y^T r, U^T r, r.r
+        double dY[2] = {0.0, 0.0}, dU[2] = {0.0, 0.0}, rr2 = 0.0, yr = 0.0;
+        for (int pt = 0; pt < ntiles; ++pt) {
+            const int s = pt % FZ_STAGES, xs = pt % FZ_XR;
+            fz_mbar_wait(xbar + xs, (pt / FZ_XR) & 1);
+            const int ncols = hn[s];
+            const int j0 = i + 1 + (g + pt * NC) * CBW;
+            double y = 0.0, r = 0.0;
+            if (lane < ncols) {
+                double tsum = 0.0;
+                for (unsigned rk = 0; rk < CS; ++rk) tsum += xsum[(xs * FZ_MAXCS + (int)rk) * FZ_CBW_MAX + lane];
+                const double aij = haij[s * FZ_CBW_MAX + lane];
+                y = 2.0 * ((tsum + snu * aij) * inv - hcorr[s * FZ_CBW_MAX + lane]);
+                r = aij - hg[s * FZ_CBW_MAX + lane] - vi * y;
+                rq[s * FZ_CBW_MAX + lane] = r;
+            }
+            __syncwarp();
+            if (lane == 0) fz_mbar_arrive(rbar + s);
+            if (crank == 0) {
+                if (lane < ncols) {
+                    a.Q[(j0 + lane) + (long)k * a.ldq] = y;
+                    a.rv[j0 + lane] = r;
+                }
+#pragma unroll
+                for (int q = 0; q < CBW; ++q) {
+                    const double rb = __shfl_sync(0xffffffffu, r, q), yb = __shfl_sync(0xffffffffu, y, q);
+                    if (q < ncols) {
+                        const double *qr = qrow + (size_t)(s * FZ_CBW_MAX + q) * 2 * NBMAX;
+#pragma unroll
+                        for (int z = 0; z < 2; ++z) {
+                            const int kk = lane + 32 * z;
+                            if (kk < k) { dY[z] += qr[kk] * rb; dU[z] += qr[NBMAX + kk] * rb; }
+                        }
+                        rr2 += rb * rb;
+                        yr += yb * rb;
+                    }
+                }
+            }
+        }
+        if (crank == 0) {
+            double *out = a.dots2p + (long)g * S2;
+#pragma unroll
+            for (int z = 0; z < 2; ++z) {
+                const int kk = lane + 32 * z;
+                if (kk < k) { out[kk] = dY[z]; out[nb + kk] = dU[z]; }
+            }
+            if (lane == 0) { out[k] = yr; out[2 * nb] = rr2; }
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) {
+                const unsigned old = atomicAdd(a.counter, 1u);
+                hn[FZ_STAGES] = (old == (unsigned)(NC - 1)) ? 1 : 0;
+            }
+        }
+    } else if (warp < FZ_W_S2) {
+        // ============================== sweep-1 warps ==============================
+        // column dots with c: t1_j = sum_r A[r,j] c[r] over this CTA's rows; c lives in registers.
+        // No barrier between the warps: each one runs ahead to the next tile as soon as it has landed.
+        const int wig = warp - FZ_W_S1;
+        const int gt = wig * 32 + lane;
+        double2 creg[RPT];
 #pragma unroll
         for (int u = 0; u < RPT; ++u) {
-            const int lr = 2 * ct + 1024 * u;
+            const int lr = 2 * gt + 2 * FZ_GT * u;
             creg[u] = (lr < len) ? *reinterpret_cast<const double2 *>(a.c + rs + lr) : make_double2(0.0, 0.0);
-            acc[u] = make_double2(0.0, 0.0);
         }
         if (g == 0) {
             // the reflector itself: v = (c + s*nu*e_i) * inv, in place and into the V panel
 #pragma unroll
             for (int u = 0; u < RPT; ++u) {
-                const int lr = 2 * ct + 1024 * u;
+                const int lr = 2 * gt + 2 * FZ_GT * u;
                 if (lr < len) {
                     const int r = rs + lr;
                     if (r >= i && r < a.m) {
@@ -302,150 +419,89 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
                 }
             }
         }
-        double dY[2] = {0.0, 0.0}, dU[2] = {0.0, 0.0}, rr2 = 0.0, yr = 0.0;
-        const bool colwarp = (cw == 0);
-
-        for (int nt = 0; nt < ntiles + FZ_D; ++nt) {
-            if (nt < ntiles) {
-                // ---- part A of tile nt: sweep 1 (column dots with c) and the cluster exchange
-                const int s = nt % FZ_STAGES;
-                fz_mbar_wait(full + s, (nt / FZ_STAGES) & 1);
-                const int ncols = hn[s];
-                const double *tl = tile + (size_t)s * FZ_STAGE;
-                double psum[CBW];
+        for (int nt = 0; nt < ntiles; ++nt) {
+            const int s = nt % FZ_STAGES;
+            fz_mbar_wait(full + s, (nt / FZ_STAGES) & 1);
+            const int ncols = hn[s];
+            const double *tl = tile + (size_t)s * FZ_STAGE;
 #pragma unroll
-                for (int q = 0; q < CBW; ++q) {
-                    psum[q] = 0.0;
-                    if (q < ncols) {
+            for (int q = 0; q < CBW; ++q) {
+                double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;      // independent chains
+                if (q < ncols) {
 #pragma unroll
-                        for (int u = 0; u < RPT; ++u) {
-                            const int lr = 2 * ct + 1024 * u;
-                            if (lr < len) {
-                                const double2 av = *reinterpret_cast<const double2 *>(tl + (size_t)q * Lc + lr);
-                                psum[q] += av.x * creg[u].x + av.y * creg[u].y;
-                            }
-                        }
-                    }
-                    psum[q] = warp_sum(psum[q]);
-                }
-                if (lane == 0) {
-#pragma unroll
-                    for (int q = 0; q < CBW; ++q) wsum[((nt & 1) * FZ_CW + cw) * 8 + q] = psum[q];
-                }
-                fz_consumer_bar();
-                if (colwarp) {
-                    const int xs = nt % FZ_XR;
-                    // fixed-shape shuffle tree over the 16 per-warp partials of every column
-                    double vals[CBW];
-#pragma unroll
-                    for (int qq = 0; qq < CBW; ++qq) {
-                        double v = (lane < FZ_CW) ? wsum[((nt & 1) * FZ_CW + lane) * 8 + qq] : 0.0;
-                        vals[qq] = warp_sum(v);
-                    }
-                    if (CS == 1) {
-                        if (lane == 0) {
-#pragma unroll
-                            for (int qq = 0; qq < CBW; ++qq) xsum[(xs * FZ_MAXCS) * 8 + qq] = vals[qq];
-                        }
-                        __syncwarp();
-                        if (lane == 0) fz_mbar_arrive(xbar + xs);
-                    } else {
-                        // every CTA of the cluster receives CBW sums from each of the CS CTAs
-                        if (lane == 0) fz_mbar_arrive_expect_tx(xbar + xs, CS * CBW * 8u);
-                        if (lane < (int)CS) {
-                            const unsigned base = fz_mapa(fz_smem_u32(xsum + (xs * FZ_MAXCS + (int)crank) * 8), (unsigned)lane);
-                            const unsigned rbar = fz_mapa(fz_smem_u32(xbar + xs), (unsigned)lane);
-#pragma unroll
-                            for (int qq = 0; qq < CBW; ++qq) fz_st_async(base + 8u * qq, vals[qq], rbar);
+                    for (int u = 0; u < RPT; ++u) {
+                        const int lr = 2 * gt + 2 * FZ_GT * u;
+                        if (lr < len) {
+                            const double2 av = *reinterpret_cast<const double2 *>(tl + (size_t)q * Lc + lr);
+                            if (u & 1) { p2 += av.x * creg[u].x; p3 += av.y * creg[u].y; }
+                            else       { p0 += av.x * creg[u].x; p1 += av.y * creg[u].y; }
                         }
                     }
                 }
+                const double ps = warp_sum((p0 + p1) + (p2 + p3));
+                if (lane == 0) wsum[(s * FZ_GW + wig) * FZ_CBW_MAX + q] = ps;
             }
-            if (nt >= FZ_D) {
-                // ---- part B of tile nt-FZ_D: y, r per column, sweep 2 (row dots with r)
-                const int pt = nt - FZ_D;
-                const int s = pt % FZ_STAGES, xs = pt % FZ_XR;
-                fz_mbar_wait(xbar + xs, (pt / FZ_XR) & 1);
-                const int ncols = hn[s];
-                const double *tl = tile + (size_t)s * FZ_STAGE;
-                const int j0 = i + 1 + (g + pt * NC) * CBW;
-#pragma unroll
-                for (int q = 0; q < CBW; ++q) {
-                    if (q < ncols) {
-                        double tsum = 0.0;
-                        for (unsigned rk = 0; rk < CS; ++rk) tsum += xsum[(xs * FZ_MAXCS + (int)rk) * 8 + q];
-                        const double aij = haij[s * 8 + q];
-                        const double y = 2.0 * ((tsum + snu * aij) * inv - hcorr[s * 8 + q]);
-                        const double r = aij - hg[s * 8 + q] - vi * y;
-#pragma unroll
-                        for (int u = 0; u < RPT; ++u) {
-                            const int lr = 2 * ct + 1024 * u;
-                            if (lr < len) {
-                                const double2 av = *reinterpret_cast<const double2 *>(tl + (size_t)q * Lc + lr);
-                                acc[u].x += av.x * r;
-                                acc[u].y += av.y * r;
-                            }
-                        }
-                        if (colwarp && crank == 0) {
-                            if (lane == 0) {
-                                a.Q[(j0 + q) + (long)k * a.ldq] = y;
-                                a.rv[j0 + q] = r;
-                            }
-                            const double *qr = qrow + (size_t)(s * FZ_CBW_MAX + q) * 2 * NBMAX;
-#pragma unroll
-                            for (int z = 0; z < 2; ++z) {
-                                const int kk = lane + 32 * z;
-                                if (kk < k) { dY[z] += qr[kk] * r; dU[z] += qr[NBMAX + kk] * r; }
-                            }
-                            rr2 += r * r;
-                            yr += y * r;
-                        }
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) fz_mbar_arrive(empty + s);
-            }
+            __syncwarp();
+            if (lane == 0) fz_mbar_arrive(wbar + s);
         }
-
-        // ---- epilogue: partial t2 of this cluster, partial panel dots, last-cluster combine
+    } else {
+        // ============================== sweep-2 warps ==============================
+        // row dots with r: t2[r] += sum_j A[r,j] r_j; the accumulators live in registers
+        const int wig = warp - FZ_W_S2;
+        const int gt = wig * 32 + lane;
+        double2 acc[RPT];
+#pragma unroll
+        for (int u = 0; u < RPT; ++u) acc[u] = make_double2(0.0, 0.0);
+        for (int nt = 0; nt < ntiles; ++nt) {
+            const int s = nt % FZ_STAGES;
+            fz_mbar_wait(rbar + s, (nt / FZ_STAGES) & 1);
+            const int ncols = hn[s];
+            const double *tl = tile + (size_t)s * FZ_STAGE;
+#pragma unroll
+            for (int q = 0; q < CBW; ++q) {
+                if (q < ncols) {
+                    const double r = rq[s * FZ_CBW_MAX + q];
+#pragma unroll
+                    for (int u = 0; u < RPT; ++u) {
+                        const int lr = 2 * gt + 2 * FZ_GT * u;
+                        if (lr < len) {
+                            const double2 av = *reinterpret_cast<const double2 *>(tl + (size_t)q * Lc + lr);
+                            acc[u].x += av.x * r;
+                            acc[u].y += av.y * r;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) fz_mbar_arrive(empty + s);
+        }
 #pragma unroll
         for (int u = 0; u < RPT; ++u) {
-            const int lr = 2 * ct + 1024 * u;
+            const int lr = 2 * gt + 2 * FZ_GT * u;
             if (lr < len) *reinterpret_cast<double2 *>(a.tmpN + (long)g * a.ldt + rs + lr) = acc[u];
         }
-        const int S2 = 2 * nb + 2;
-        if (colwarp && crank == 0) {
-            double *out = a.dots2p + (long)g * S2;
-#pragma unroll
-            for (int z = 0; z < 2; ++z) {
-                const int kk = lane + 32 * z;
-                if (kk < k) { out[kk] = dY[z]; out[nb + kk] = dU[z]; }
-            }
-            if (lane == 0) { out[k] = yr; out[2 * nb] = rr2; }
-            __threadfence();
-            __syncwarp();
-            if (lane == 0) {
-                const unsigned old = atomicAdd(a.counter, 1u);
-                hn[FZ_STAGES] = (old == (unsigned)(NC - 1)) ? 1 : 0;
-            }
-        }
-        fz_consumer_bar();
-        if (hn[FZ_STAGES]) {
-            __threadfence();
-            // entries: [0..k] Y^T r, [nb..nb+k) U^T r, [2nb] r.r  -> 2k+2 values, 2 threads each
-            const int e = ct >> 1, half = ct & 1, ne = 2 * k + 2;
-            const int slot = (e <= k) ? e : (e <= 2 * k ? nb + (e - k - 1) : 2 * nb);
-            double sacc = 0.0;
-            if (e < ne) {
-                const int h0 = half ? (NC + 1) / 2 : 0, h1 = half ? NC : (NC + 1) / 2;
-                for (int p2 = h0; p2 < h1; ++p2) sacc += __ldcg(a.dots2p + (long)p2 * S2 + slot);
-            }
-            const double other = __shfl_xor_sync(0xffffffffu, sacc, 1);
-            if (e < ne && half == 0) a.dots2[slot] = sacc + other;
-            if (ct == 0) *a.counter = 0u;
-        }
     }
-    fz_cluster_sync();      // nobody exits while a peer may still write into its shared memory
+
+    // ---- last-cluster combine of the panel-dot partials (fixed order, all threads of that CTA help)
+    __syncthreads();
+    if (hn[FZ_STAGES]) {
+        __threadfence();
+        const int ne = 2 * k + 2;                      // [0..k] Y^T r, [nb..nb+k) U^T r, [2nb] r.r
+        const int e = tid >> 2, part = tid & 3;        // 4 threads per entry (672/4 = 168 >= 130)
+        const int slot = (e <= k) ? e : (e <= 2 * k ? nb + (e - k - 1) : 2 * nb);
+        double sacc = 0.0;
+        if (e < ne) {
+            const int chunk = (NC + 3) / 4;
+            const int p0 = part * chunk, p1 = min(NC, p0 + chunk);
+#pragma unroll 8
+            for (int p2 = p0; p2 < p1; ++p2) sacc += __ldcg(a.dots2p + (long)p2 * S2 + slot);
+        }
+        sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+        sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+        if (e < ne && part == 0) a.dots2[slot] = sacc;
+        if (tid == 0) *a.counter = 0u;
+    }
+    if (CS > 1) fz_cluster_sync();      // nobody exits while a peer may still write into its shared memory
 }
 
 } // namespace svdgpu
