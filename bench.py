@@ -194,6 +194,9 @@ def run_own(args):
     L = D.lib()
     L.svdgpu_set_device(local)
     if world > 1:
+        # keep stdout to the one JSON line: NCCL prints its version banner there at VERSION/INFO level
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", ""):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     n = m = args.n
@@ -368,6 +371,22 @@ def run_own(args):
         e2e = {"value": float(tt.item()) / args.steps, "unit": UNIT, "h2d_bytes_per_step": m * n * 8,
                "d2h_bytes_per_step": (m + n) * mn * 8}
 
+    check = None
+    if args.check and rank == 0 and n <= 8192:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import util
+        step_device() if world == 1 else None
+        torch.cuda.synchronize()
+        if world == 1:
+            sg, Uh, Vh = sigma.cpu().numpy(), U.cpu().numpy().T, V.cpu().numpy().T
+        else:
+            sg, Uh, Vh = sig_full[:mn].cpu().numpy(), Ufull[:mn].cpu().numpy().T, Vfull[:mn].cpu().numpy().T
+        check = util.svd_metrics(A_host, sg, Uh, Vh)
+        check["eps_n"] = float(np.finfo(np.float64).eps * n)
+    if args.check and world > 1:
+        if rank != 0:
+            pass
+        dist.barrier()
     if rank == 0:
         line = {"metric": METRIC, "value": ms_per_step * 1e-3, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "strong",
@@ -378,6 +397,8 @@ def run_own(args):
                            "parallelism": "1 GPU" if world == 1 else
                            f"bidiag+dDC on rank 0, vectors/back-transform sharded over {world} ranks"},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+        if check:
+            line["check_vs_lapack"] = check
         if phase:
             line["phases"] = phase
         if roof:
@@ -398,6 +419,7 @@ def main():
     ap.add_argument("--n", type=int, default=int(os.environ.get("SVD_BENCH_N", "4096")))
     ap.add_argument("--cpu-n", type=int, default=1024, help="size of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--check", action="store_true", help="verify the last step's result against LAPACK (n <= 8192)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -191,6 +191,7 @@ __device__ __forceinline__ Refl make_refl(double x0, double nrm2)
 // handles panel columns q = w, w+8, ... and split partials s = w, w+8, ...; the slices are
 // combined through shared memory in a fixed order (deterministic).
 constexpr int FK_SLICES = 8;
+constexpr int DOT_SLOTS_C = 2 * NBMAX + 2;
 
 // finish_y: after gemvT of step i (panel column k).
 //   blocks [0, nColBlk): 32 trailing columns each -> y_j (new Y column), r_j (row i after H)
@@ -415,6 +416,163 @@ finish_x_kernel(double *__restrict__ A, long lda, int i, int m, int n, int k, in
     }
 }
 
+// finish_xf: finish_x for the fused path.  1024 threads = 32 rows (lanes) x 32 panel slices (warps);
+// a CTA walks RB row groups.  Both partial-dot reductions live in the consumers' prologues: this
+// kernel first combines the fused pass's per-cluster partials [Y^T r | U^T r | r.r] (fixed order),
+// and leaves per-CTA partials [V^T c' | X^T c' | c'.c'] for the next fused pass to combine — no
+// atomics, no fences, no serial "last block".
+constexpr int XF_SL = 32;
+template <int RB>
+__global__ void __launch_bounds__(1024)
+finish_xf_kernel(double *__restrict__ A, long lda, int i, int m, int n, int k, int nb,
+                 double *__restrict__ P, long ldp, double *__restrict__ Q, long ldq,
+                 double *__restrict__ c, const double *__restrict__ rv,
+                 const double *__restrict__ tmp, long ldt, int nsplit,
+                 const double *__restrict__ dots2p, int nparts2, double *__restrict__ beta, int nRowBlk,
+                 double *__restrict__ dots1p)
+{
+    constexpr int S = DOT_SLOTS_C;
+    __shared__ double s_part[7][S];
+    __shared__ double s_d[S];
+    __shared__ double s_yTu[NBMAX], s_uTu[NBMAX], s_rowY[NBMAX], s_rowU[NBMAX];
+    __shared__ double s_red[3][XF_SL][33];
+    __shared__ double s_red2[3][8][32];
+    __shared__ double s_c[32], s_x[32];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int R = n - i - 1, Lb = m - i - 1;
+    const bool rowblk = (int)blockIdx.x < nRowBlk;
+    constexpr int ZV = NBMAX / XF_SL + 1, ZX = NBMAX / XF_SL;       // 3, 2
+
+    // ---- loads that depend on nothing: first row group, the row of Q, r_first
+    int idx = blockIdx.x * (32 * RB) + lane;
+    bool live = rowblk && idx < Lb;
+    double vk[ZV], xk[ZX], tt = 0.0, ar = 0.0;
+#pragma unroll
+    for (int z = 0; z < ZV; ++z) { const int q = w + XF_SL * z; vk[z] = (live && q <= k) ? P[(i + 1 + idx) + (long)q * ldp] : 0.0; }
+#pragma unroll
+    for (int z = 0; z < ZX; ++z) { const int q = w + XF_SL * z; xk[z] = (live && q < k) ? P[(i + 1 + idx) + (long)(nb + q) * ldp] : 0.0; }
+    if (live) {
+        for (int sp = w; sp < nsplit; sp += XF_SL) tt += tmp[(long)sp * ldt + i + 1 + idx];
+        if (w == 0) ar = A[(i + 1 + idx) + (long)(i + 1) * lda];
+    }
+    const double rf = rv[i + 1];
+    double qy = 0.0, qu = 0.0;
+    if (t <= k) qy = Q[(i + 1) + (long)t * ldq];
+    if (t < k) qu = Q[(i + 1) + (long)(nb + t) * ldq];
+    // ---- combine the pass's partial dots: entries [0..k], [nb..nb+k), [2nb]; 7 threads per entry
+    {
+        const int ne = 2 * k + 2, e = t / 7, part = t - 7 * e;
+        if (e < ne) {
+            const int slot = (e <= k) ? e : (e <= 2 * k ? nb + (e - k - 1) : 2 * nb);
+            const int chunk = (nparts2 + 6) / 7, p0 = part * chunk, p1 = min(nparts2, p0 + chunk);
+            double a2 = 0.0;
+            for (int pz = p0; pz < p1; ++pz) a2 += dots2p[(long)pz * S + slot];
+            s_part[part][slot] = a2;
+        }
+    }
+    __syncthreads();
+    if (t < S && (t <= k || (t >= nb && t < nb + k) || t == 2 * nb)) {
+        double a2 = 0.0;
+#pragma unroll
+        for (int pz = 0; pz < 7; ++pz) a2 += s_part[pz][t];
+        s_d[t] = a2;
+    }
+    __syncthreads();
+    const Refl f = make_refl(rf, s_d[2 * nb]);
+    const double ufirst = (rf + f.snu) * f.inv;
+    if (!rowblk) {
+        // ---- column part: the row reflector itself
+        const int cidx = (blockIdx.x - nRowBlk) * 1024 + t;
+        if (cidx == 0) beta[i] = -f.snu;
+        if (cidx < R) {
+            const int j = i + 1 + cidx;
+            const double u = (rv[j] + (cidx == 0 ? f.snu : 0.0)) * f.inv;
+            A[i + (long)j * lda] = u;
+            Q[j + (long)(nb + k) * ldq] = u;
+        }
+        return;
+    }
+    if (t <= k) { s_rowY[t] = qy; s_yTu[t] = (s_d[t] + f.snu * qy) * f.inv; }
+    if (t < k) { s_rowU[t] = qu; s_uTu[t] = (s_d[nb + t] + f.snu * qu) * f.inv; }
+    __syncthreads();
+
+    double dv[ZV], dx[ZV], cc2 = 0.0;
+#pragma unroll
+    for (int z = 0; z < ZV; ++z) { dv[z] = 0.0; dx[z] = 0.0; }
+#pragma unroll 1
+    for (int rb = 0; rb < RB; ++rb) {
+        if (rb > 0) {
+            idx = blockIdx.x * (32 * RB) + rb * 32 + lane;
+            live = idx < Lb;
+            tt = 0.0; ar = 0.0;
+#pragma unroll
+            for (int z = 0; z < ZV; ++z) { const int q = w + XF_SL * z; vk[z] = (live && q <= k) ? P[(i + 1 + idx) + (long)q * ldp] : 0.0; }
+#pragma unroll
+            for (int z = 0; z < ZX; ++z) { const int q = w + XF_SL * z; xk[z] = (live && q < k) ? P[(i + 1 + idx) + (long)(nb + q) * ldp] : 0.0; }
+            if (live) {
+                for (int sp = w; sp < nsplit; sp += XF_SL) tt += tmp[(long)sp * ldt + i + 1 + idx];
+                if (w == 0) ar = A[(i + 1 + idx) + (long)(i + 1) * lda];
+            }
+        }
+        const int r = i + 1 + idx;
+        double corr = 0.0, sub = 0.0;
+#pragma unroll
+        for (int z = 0; z < ZV; ++z) { const int q = w + XF_SL * z; if (q <= k) { corr += vk[z] * s_yTu[q]; sub += vk[z] * s_rowY[q]; } }
+#pragma unroll
+        for (int z = 0; z < ZX; ++z) { const int q = w + XF_SL * z; if (q < k) { corr += xk[z] * s_uTu[q]; sub += xk[z] * s_rowU[q]; } }
+        s_red[0][w][lane] = corr; s_red[1][w][lane] = sub; s_red[2][w][lane] = tt;
+        __syncthreads();
+        if (w < 8) {
+#pragma unroll
+            for (int qn = 0; qn < 3; ++qn)
+                s_red2[qn][w][lane] = (s_red[qn][4 * w][lane] + s_red[qn][4 * w + 1][lane]) +
+                                      (s_red[qn][4 * w + 2][lane] + s_red[qn][4 * w + 3][lane]);
+        }
+        __syncthreads();
+        if (w == 0) {
+            double cc = 0.0, x = 0.0;
+            if (live) {
+                corr = 0.0; sub = 0.0; tt = 0.0;
+#pragma unroll
+                for (int z = 0; z < 8; ++z) { corr += s_red2[0][z][lane]; sub += s_red2[1][z][lane]; tt += s_red2[2][z][lane]; }
+                x = 2.0 * ((tt + f.snu * ar) * f.inv - corr);
+                P[r + (long)(nb + k) * ldp] = x;
+                cc = ar - sub - x * ufirst;
+                c[r] = cc;
+            }
+            s_c[lane] = cc;
+            s_x[lane] = x;
+            cc2 += cc * cc;
+            if (blockIdx.x == 0 && rb == 0 && lane == 0) c[i] = 0.0;   // keeps the 128-bit loads of the next pass harmless
+        }
+        __syncthreads();
+        const double cl = s_c[lane];
+#pragma unroll
+        for (int z = 0; z < ZV; ++z) {
+            const int q = w + XF_SL * z;
+            if (q <= k) {
+                const double xv = (q < k) ? xk[z < ZX ? z : 0] : s_x[lane];
+                dv[z] += vk[z] * cl;
+                dx[z] += xv * cl;
+            }
+        }
+    }
+    // ---- this CTA's partial [V^T c' | X^T c' | c'.c'] (each warp owns its panel columns)
+    double *out = dots1p + (long)blockIdx.x * S;
+#pragma unroll
+    for (int z = 0; z < ZV; ++z) {
+        const int q = w + XF_SL * z;
+        if (q <= k) {                                       // warp-uniform
+            const double a2 = warp_sum(dv[z]), b2 = warp_sum(dx[z]);
+            if (lane == 0) { out[q] = a2; out[nb + q] = b2; }
+        }
+    }
+    if (w == 0) {
+        const double a2 = warp_sum(cc2);
+        if (lane == 0) out[2 * nb] = a2;
+    }
+}
+
 __global__ void col_init_kernel(const double *__restrict__ A, int m, long lda, double *__restrict__ c)
 {
     long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -440,7 +598,7 @@ size_t bidiag_workspace_bytes(int m, int n, long lda)
     d += (size_t)BIDIAG_MAX_SPLIT * ldq;   // tmpT
     d += (size_t)TMPN_ROWS * lda;          // tmpN
     d += 2 * DOT_SLOTS;                    // dots1, dots2 (final)
-    d += (size_t)(ceil_div(m, 128) + 1) * DOT_SLOTS;   // dots1 partials (finish_x<4> row blocks)
+    d += (size_t)(ceil_div(m, 128) + 130) * DOT_SLOTS; // dots1 partials (finish_xf row blocks)
     d += (size_t)FZ_MAX_CLUSTERS * DOT_SLOTS;          // dots2 partials (fused pass clusters)
     d += 8;                                // counters
     return d * sizeof(double);
@@ -464,7 +622,7 @@ static BidiagBufs carve(void *workspace, int m, int n, long lda)
     b.tmpN = w;   w += (size_t)TMPN_ROWS * lda;
     b.dots1 = w;  w += DOT_SLOTS;
     b.dots2 = w;  w += DOT_SLOTS;
-    b.dots1p = w; w += (size_t)(ceil_div(m, 128) + 1) * DOT_SLOTS;
+    b.dots1p = w; w += (size_t)(ceil_div(m, 128) + 130) * DOT_SLOTS;
     b.dots2p = w; w += (size_t)FZ_MAX_CLUSTERS * DOT_SLOTS;
     b.counters = (unsigned *)w;
     return b;
@@ -607,7 +765,8 @@ void bidiag_device(int m, int n, double *A, long lda, double *alpha, double *bet
     // thresholds below which the split passes are used (overridable for tests)
     const char *e1 = getenv("SVD_GPU_FUSED_MIN_ROWS"), *e2 = getenv("SVD_GPU_FUSED_MIN_COLS");
     const int fz_min_rows = e1 ? atoi(e1) : FZ_MIN_ROWS, fz_min_cols = e2 ? atoi(e2) : FZ_MIN_COLS;
-    bool dots1_ready = false;       // dots1 (final) matches the current column c
+    bool dots1_ready = false;       // dots1p holds dots1_parts partial dot vectors of the current column c
+    int dots1_parts = 0;
 
     SVD_CUDA_CHECK(cudaMemsetAsync(b.rv, 0, sizeof(double) * ((size_t)b.ldq + 2), st));
     SVD_CUDA_CHECK(cudaMemsetAsync(b.dots1, 0, sizeof(double) * 2 * DOT_SLOTS, st));
@@ -636,19 +795,22 @@ void bidiag_device(int m, int n, double *A, long lda, double *alpha, double *bet
             FusedArgs fa;
             fa.A = A; fa.lda = lda; fa.i = i; fa.m = m; fa.n = n; fa.mpad = mpad; fa.k = k; fa.nb = nb;
             fa.P = b.P; fa.ldp = b.ldp; fa.Q = b.Q; fa.ldq = b.ldq; fa.c = b.c; fa.rv = b.rv;
-            fa.tmpN = b.tmpN; fa.ldt = lda; fa.dots1 = b.dots1; fa.dots2p = b.dots2p; fa.dots2 = b.dots2;
-            fa.counter = b.counters; fa.alpha = alpha; fa.T = pl.T; fa.NC = pl.NC; fa.Lc = pl.Lc;
+            fa.tmpN = b.tmpN; fa.ldt = lda;
+            fa.dots1 = dots1_ready ? b.dots1p : b.dots1; fa.nparts1 = dots1_ready ? dots1_parts : 0;
+            fa.dots2p = b.dots2p; fa.alpha = alpha; fa.T = pl.T; fa.NC = pl.NC; fa.Lc = pl.Lc;
             launch_fused(fa, pl, st);
-            if (Lb > 2048) {
+            if (Lb > 4096) {
                 const int nRowBlk = ceil_div(Lb, 128), nColBlk = ceil_div(R, 1024);
-                finish_x_kernel<4><<<nRowBlk + nColBlk, 1024, 0, st>>>(A, lda, i, m, n, k, nb, 1, b.P, b.ldp, b.Q,
-                                                                       b.ldq, b.c, b.rv, b.tmpN, lda, pl.NC, b.dots2,
-                                                                       beta, nRowBlk, b.dots1p, b.dots1, b.counters + 1);
+                finish_xf_kernel<4><<<nRowBlk + nColBlk, 1024, 0, st>>>(A, lda, i, m, n, k, nb, b.P, b.ldp, b.Q, b.ldq,
+                                                                        b.c, b.rv, b.tmpN, lda, pl.NC, b.dots2p, pl.NC,
+                                                                        beta, nRowBlk, b.dots1p);
+                dots1_parts = nRowBlk;
             } else {
-                const int nRowBlk = ceil_div(Lb, 32), nColBlk = ceil_div(R, 256);
-                finish_x_kernel<1><<<nRowBlk + nColBlk, 256, 0, st>>>(A, lda, i, m, n, k, nb, 1, b.P, b.ldp, b.Q,
-                                                                      b.ldq, b.c, b.rv, b.tmpN, lda, pl.NC, b.dots2,
-                                                                      beta, nRowBlk, b.dots1p, b.dots1, b.counters + 1);
+                const int nRowBlk = ceil_div(Lb, 32), nColBlk = ceil_div(R, 1024);
+                finish_xf_kernel<1><<<nRowBlk + nColBlk, 1024, 0, st>>>(A, lda, i, m, n, k, nb, b.P, b.ldp, b.Q, b.ldq,
+                                                                        b.c, b.rv, b.tmpN, lda, pl.NC, b.dots2p, pl.NC,
+                                                                        beta, nRowBlk, b.dots1p);
+                dots1_parts = nRowBlk;
             }
             SVD_KERNEL_CHECK();
             dots1_ready = true;

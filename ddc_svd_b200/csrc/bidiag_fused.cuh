@@ -26,8 +26,8 @@
 //     exchanged through distributed shared memory (st.async ... mbarrier::complete_tx on the
 //     remote barrier, so receivers need no cluster-scope acquire);
 //   * clusters walk the column tiles round-robin; every cluster writes its partial t2 and its
-//     partial panel dots; the last cluster to finish combines the dot partials in a fixed
-//     order (deterministic, no floating-point atomics).
+//     partial panel dots; the consumer kernel (finish_xf) combines the partials in a fixed order
+//     in its prologue (deterministic: no floating-point atomics, no fences, no serial tail).
 #pragma once
 
 namespace svdgpu {
@@ -69,10 +69,9 @@ struct FusedArgs {
     const double *c;
     double *rv;
     double *tmpN; long ldt;       // [cluster][row]: partial A r
-    const double *dots1;          // final [V^T c | X^T c | c.c]
-    double *dots2p;               // [cluster][2nb+2] partials
-    double *dots2;                // final [Y^T r | U^T r | r.r]
-    unsigned *counter;
+    const double *dots1;          // [V^T c | X^T c | c.c]: final (nparts1 == 0) or nparts1 partial vectors
+    int nparts1;                  //   of stride 2*NBMAX+2 left by finish_xf, combined in the prologue here
+    double *dots2p;               // [cluster][2*NBMAX+2] partials of [Y^T r | U^T r | r.r] for finish_xf
     double *alpha;
     int T, NC, Lc;                // column tiles, clusters, rows per CTA (even)
 };
@@ -208,29 +207,53 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
             fz_mbar_init(rbar + s, 1);          // finisher
         }
         for (int x = 0; x < FZ_XR; ++x) fz_mbar_init(xbar + x, 1);
-        hn[FZ_STAGES] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (tid == 32) {
-        const double ci = a.c[i];
-        Refl f = make_refl(ci, a.dots1[2 * nb]);
-        s_sc[0] = f.snu; s_sc[1] = f.inv; s_sc[2] = (ci + f.snu) * f.inv;
-        if (g == 0 && crank == 0) a.alpha[i] = -f.snu;
+    // ---- combine the partial dots of the current column c (left by finish_xf) in a fixed order;
+    //      the tile area is still unused and serves as scratch
+    {
+        constexpr int S1 = 2 * NBMAX + 2;
+        double *s_part = tile, *s_d1 = tile + 5 * S1;
+        const int ne = 2 * k + 1;                         // [0..k) V^T c, [nb..nb+k) X^T c, [2nb] c.c
+        if (a.nparts1 > 0) {
+            const int e = tid / 5, part = tid - 5 * e;    // 5 threads per entry (672/5 = 134 >= 129)
+            if (e < ne) {
+                const int slot = (e < k) ? e : (e < 2 * k ? nb + (e - k) : 2 * nb);
+                const int chunk = (a.nparts1 + 4) / 5, p0 = part * chunk, p1 = min(a.nparts1, p0 + chunk);
+                double a2 = 0.0;
+                for (int pz = p0; pz < p1; ++pz) a2 += a.dots1[(long)pz * S1 + slot];
+                s_part[part * S1 + slot] = a2;
+            }
+            __syncthreads();
+            if (tid < S1 && (tid < k || (tid >= nb && tid < nb + k) || tid == 2 * nb))
+                s_d1[tid] = ((s_part[tid] + s_part[S1 + tid]) + (s_part[2 * S1 + tid] + s_part[3 * S1 + tid])) +
+                            s_part[4 * S1 + tid];
+        } else {
+            if (tid < S1 && (tid < k || (tid >= nb && tid < nb + k) || tid == 2 * nb)) s_d1[tid] = a.dots1[tid];
+        }
+        __syncthreads();
+        if (tid == 32) {
+            const double ci = a.c[i];
+            Refl f = make_refl(ci, s_d1[2 * nb]);
+            s_sc[0] = f.snu; s_sc[1] = f.inv; s_sc[2] = (ci + f.snu) * f.inv;
+            if (g == 0 && crank == 0) a.alpha[i] = -f.snu;
+        }
+        __syncthreads();
+        if (tid < k) {
+            const double snu0 = s_sc[0], inv0 = s_sc[1];
+            const double pv = a.P[i + (long)tid * a.ldp], px = a.P[i + (long)(nb + tid) * a.ldp];
+            s_rowV[tid] = pv;
+            s_rowX[tid] = px;
+            s_vTv[tid] = (s_d1[tid] + snu0 * pv) * inv0;
+            s_xTv[tid] = (s_d1[nb + tid] + snu0 * px) * inv0;
+        }
+        __syncthreads();
     }
-    __syncthreads();
     const double snu = s_sc[0], inv = s_sc[1], vi = s_sc[2];
-    if (tid < k) {
-        const double pv = a.P[i + (long)tid * a.ldp], px = a.P[i + (long)(nb + tid) * a.ldp];
-        s_rowV[tid] = pv;
-        s_rowX[tid] = px;
-        s_vTv[tid] = (a.dots1[tid] + snu * pv) * inv;
-        s_xTv[tid] = (a.dots1[nb + tid] + snu * px) * inv;
-    }
-    __syncthreads();
     if (CS > 1) fz_cluster_sync();                         // barriers exist everywhere before remote traffic
 
     const int ntiles = (a.T > g) ? (a.T - g + NC - 1) / NC : 0;
-    const int S2 = 2 * nb + 2;
+    constexpr int S2 = 2 * NBMAX + 2;
 
     if (warp == 0) {
         // ============================ TMA producer warp ============================
@@ -380,12 +403,6 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
                 if (kk < k) { out[kk] = dY[z]; out[nb + kk] = dU[z]; }
             }
             if (lane == 0) { out[k] = yr; out[2 * nb] = rr2; }
-            __threadfence();
-            __syncwarp();
-            if (lane == 0) {
-                const unsigned old = atomicAdd(a.counter, 1u);
-                hn[FZ_STAGES] = (old == (unsigned)(NC - 1)) ? 1 : 0;
-            }
         }
     } else if (warp < FZ_W_S2) {
         // ============================== sweep-1 warps ==============================
@@ -482,25 +499,6 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
         }
     }
 
-    // ---- last-cluster combine of the panel-dot partials (fixed order, all threads of that CTA help)
-    __syncthreads();
-    if (hn[FZ_STAGES]) {
-        __threadfence();
-        const int ne = 2 * k + 2;                      // [0..k] Y^T r, [nb..nb+k) U^T r, [2nb] r.r
-        const int e = tid >> 2, part = tid & 3;        // 4 threads per entry (672/4 = 168 >= 130)
-        const int slot = (e <= k) ? e : (e <= 2 * k ? nb + (e - k - 1) : 2 * nb);
-        double sacc = 0.0;
-        if (e < ne) {
-            const int chunk = (NC + 3) / 4;
-            const int p0 = part * chunk, p1 = min(NC, p0 + chunk);
-#pragma unroll 8
-            for (int p2 = p0; p2 < p1; ++p2) sacc += __ldcg(a.dots2p + (long)p2 * S2 + slot);
-        }
-        sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
-        sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
-        if (e < ne && part == 0) a.dots2[slot] = sacc;
-        if (tid == 0) *a.counter = 0u;
-    }
     if (CS > 1) fz_cluster_sync();      // nobody exits while a peer may still write into its shared memory
 }
 
