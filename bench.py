@@ -416,7 +416,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=int(os.environ.get("SVD_BENCH_N", "4096")))
+    # (--size, not --n: torchrun's own parser treats a bare --n as an ambiguous abbreviation)
+    ap.add_argument("--size", "--n", dest="n", type=int, default=int(os.environ.get("SVD_BENCH_N", "4096")))
     ap.add_argument("--cpu-n", type=int, default=1024, help="size of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--check", action="store_true", help="verify the last step's result against LAPACK (n <= 8192)")
