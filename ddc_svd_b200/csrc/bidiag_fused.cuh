@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
     if (tid == 0) {
         for (int s = 0; s < FZ_STAGES; ++s) {
             fz_mbar_init(full + s, 2);          // TMA transaction arrive + helper
-            fz_mbar_init(empty + s, FZ_GW);     // the sweep-2 warps of the tile's group
+            fz_mbar_init(empty + s, FZ_GW + 1); // the sweep-2 warps + the finisher (it reads the stage's panel rows)
             fz_mbar_init(wbar + s, FZ_GW);      // the sweep-1 warps of the tile's group
             fz_mbar_init(rbar + s, 1);          // finisher
         }
@@ -394,6 +394,9 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
                     }
                 }
             }
+            // the stage's helper slots (qrow) are free for the next tile only now
+            __syncwarp();
+            if (lane == 0) fz_mbar_arrive(empty + s);
         }
         if (crank == 0) {
             double *out = a.dots2p + (long)g * S2;

@@ -101,6 +101,28 @@ def test_bidiag_fused_pass_vs_oracle(D, shape):
     assert np.abs(Ag - As).max() <= 1e-10 and np.abs(ag - a_s).max() <= 1e-10 * max(1.0, np.abs(ag).max())
 
 
+@pytest.mark.parametrize("shape", [(9000, 3000), (6144, 6144), (17000, 2048)])
+def test_bidiag_fused_vs_split_many_tiles(D, shape):
+    # long pipelines (tens of tiles per cluster, clusters of 1/2/4/8): the fused pass must agree with
+    # the split passes and conserve the Frobenius norm (||B||_F = ||A||_F) — catches stage-reuse races
+    m, n = shape
+    rng = np.random.default_rng(3)
+    A = np.asfortranarray(rng.uniform(1.0, 2.0, size=(m, n)))
+    fro2 = float(np.sum(A * A))
+    out = {}
+    for mode in ("1", "0"):
+        os.environ["SVD_GPU_FUSED"] = mode
+        try:
+            out[mode] = D.bidiag_par(A)
+        finally:
+            del os.environ["SVD_GPU_FUSED"]
+    (Af, af, bf), (As, a_s, b_s) = out["1"], out["0"]
+    for al, be in ((af, bf), (a_s, b_s)):
+        assert abs(np.sum(al * al) + np.sum(be * be) - fro2) <= 1e-12 * fro2
+    assert np.abs(Af - As).max() <= 1e-9
+    assert np.abs(af - a_s).max() <= 1e-9 * np.abs(a_s).max() and np.abs(bf - b_s).max() <= 1e-9 * np.abs(a_s).max()
+
+
 @pytest.mark.parametrize("shape", [(300, 200), (200, 300), (513, 512), (97, 80)])
 def test_bidiag_fused_pass_small_tiles(D, shape):
     # force the fused pass on small trailing blocks too (all tile shapes, ragged last tiles)
