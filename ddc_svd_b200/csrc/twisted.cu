@@ -91,56 +91,96 @@ tw_qd_kernel(int mb, int ns, const double *__restrict__ q, const double *__restr
 }
 
 // gamma_j = s_j + p_j + tau; twist index = argmin |gamma_j|, later index on ties
-// (which_min_gamma, parallel-twisted.c:277-284)
-__global__ void __launch_bounds__(64)
+// (which_min_gamma, parallel-twisted.c:277-284).  32 sigmas (lanes) x 8 position slices (warps);
+// every slice scans its positions with coalesced loads, the slices are merged in a fixed order.
+constexpr int TWS_SL = 8;
+__global__ void __launch_bounds__(32 * TWS_SL)
 tw_select_kernel(int mb, int ns, const double *__restrict__ tau, const double *__restrict__ S,
                  const double *__restrict__ P, int *__restrict__ kidx, double *__restrict__ gk)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= ns) return;
-    const double tv = tau[t];
+    __shared__ double s_best[TWS_SL][32], s_g[TWS_SL][32];
+    __shared__ int s_k[TWS_SL][32];
+    const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int t = blockIdx.x * 32 + lane;
     double best = DBL_MAX, bestg = 0.0;
     int bk = 0;
+    if (t < ns) {
+        const double tv = tau[t];
+        const int chunk = (mb + TWS_SL - 1) / TWS_SL;
+        const int j0 = sl * chunk, j1 = min(mb, j0 + chunk);
 #pragma unroll 8
-    for (int j = 0; j < mb; ++j) {
-        double g = S[(size_t)j * ns + t] + P[(size_t)j * ns + t] + tv;
-        double ag = fabs(g);
-        if (ag <= best) { best = ag; bestg = g; bk = j; }
+        for (int j = j0; j < j1; ++j) {
+            double g = S[(size_t)j * ns + t] + P[(size_t)j * ns + t] + tv;
+            double ag = fabs(g);
+            if (ag <= best) { best = ag; bestg = g; bk = j; }
+        }
     }
-    kidx[t] = bk;
-    gk[t] = bestg;
+    s_best[sl][lane] = best; s_g[sl][lane] = bestg; s_k[sl][lane] = bk;
+    __syncthreads();
+    if (sl == 0 && t < ns) {
+        // slices cover increasing position ranges: "<=" keeps the later index on ties
+        for (int z = 1; z < TWS_SL; ++z)
+            if (s_best[z][lane] <= best) { best = s_best[z][lane]; bestg = s_g[z][lane]; bk = s_k[z][lane]; }
+        kidx[t] = bk;
+        gk[t] = bestg;
+    }
 }
 
 // z_k = 1; j < k: z_j = -(ab_j / d+_j) z_{j+1};  j >= k: z_{j+1} = -(ab_j / d-_{j+1}) z_j
 // (TwistedFactorization, parallel-twisted.c:495-521).  z overwrites S in place.
+// All lanes walk the SAME rows (coalesced, loads batched 8 rows ahead of the serial recurrence);
+// a lane simply stays idle (z = 1) until the walk reaches its own twist index.
 __global__ void __launch_bounds__(32)
 tw_solve_kernel(int mb, int ns, const double *__restrict__ q, const double *__restrict__ e,
                 const double *__restrict__ ab, const double *__restrict__ pivmin_p,
                 const int *__restrict__ kidx, double *__restrict__ S, const double *__restrict__ P,
                 double *__restrict__ nrm2)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= ns) return;
+    const int tt = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = tt < ns;
+    const int t = valid ? tt : ns - 1;                      // idle lanes shadow a valid column, never store
     const int k = kidx[t];
     const double pivmin = *pivmin_p;
     double z = 1.0, acc = 0.0;
+    constexpr int UB = 8;
     if (blockIdx.y == 0) {
-        for (int j = k - 1; j >= 0; --j) {
-            double dp = guard_pivot(__ldg(q + j) + S[(size_t)j * ns + t], pivmin);
-            z = -(__ldg(ab + j) / dp) * z;
-            S[(size_t)j * ns + t] = z;
-            acc += z * z;
+        // downward: rows kmax-1 .. 0 (warp-uniform start), a lane is active where j < k
+        const int kmax = __reduce_max_sync(0xffffffffu, k);
+        for (int jb = min(mb - 2, kmax - 1); jb >= 0; jb -= UB) {
+            double sv[UB];
+#pragma unroll
+            for (int u = 0; u < UB; ++u) { const int j = jb - u; sv[u] = (j >= 0) ? S[(size_t)j * ns + t] : 0.0; }
+#pragma unroll
+            for (int u = 0; u < UB; ++u) {
+                const int j = jb - u;
+                if (j >= 0 && j < k) {
+                    double dp = guard_pivot(__ldg(q + j) + sv[u], pivmin);
+                    z = -(__ldg(ab + j) / dp) * z;
+                    if (valid) S[(size_t)j * ns + t] = z;
+                    acc += z * z;
+                }
+            }
         }
-        S[(size_t)k * ns + t] = 1.0;
-        nrm2[t] = acc + 1.0;
+        if (valid) { S[(size_t)k * ns + t] = 1.0; nrm2[t] = acc + 1.0; }
     } else {
-        for (int j = k; j < mb - 1; ++j) {
-            double dm = guard_pivot(__ldg(e + j) + P[(size_t)(j + 1) * ns + t], pivmin);
-            z = -(__ldg(ab + j) / dm) * z;
-            S[(size_t)(j + 1) * ns + t] = z;
-            acc += z * z;
+        // upward: rows kmin .. mb-2 write z_{j+1}, a lane is active where j >= k
+        const int kmin = __reduce_min_sync(0xffffffffu, k);
+        for (int jb = kmin; jb < mb - 1; jb += UB) {
+            double pv[UB];
+#pragma unroll
+            for (int u = 0; u < UB; ++u) { const int j = jb + u; pv[u] = (j < mb - 1) ? P[(size_t)(j + 1) * ns + t] : 0.0; }
+#pragma unroll
+            for (int u = 0; u < UB; ++u) {
+                const int j = jb + u;
+                if (j < mb - 1 && j >= k) {
+                    double dm = guard_pivot(__ldg(e + j) + pv[u], pivmin);
+                    z = -(__ldg(ab + j) / dm) * z;
+                    if (valid) S[(size_t)(j + 1) * ns + t] = z;
+                    acc += z * z;
+                }
+            }
         }
-        nrm2[ns + t] = acc;
+        if (valid) nrm2[ns + t] = acc;
     }
 }
 
@@ -249,7 +289,7 @@ void twisted_vectors_device(int n, int mb, const double *a, const double *b, con
         for (int sweep = 0; sweep <= rqi_steps; ++sweep) {
             tw_qd_kernel<<<dim3(ceil_div(c, 32), 2), 32, 0, st>>>(mb, c, q, e, tau, pivmin, S, P);
             SVD_KERNEL_CHECK();
-            tw_select_kernel<<<ceil_div(c, 64), 64, 0, st>>>(mb, c, tau, S, P, kidx, gk);
+            tw_select_kernel<<<ceil_div(c, 32), 32 * TWS_SL, 0, st>>>(mb, c, tau, S, P, kidx, gk);
             SVD_KERNEL_CHECK();
             tw_solve_kernel<<<dim3(ceil_div(c, 32), 2), 32, 0, st>>>(mb, c, q, e, ab, pivmin, kidx, S, P, nrm2);
             SVD_KERNEL_CHECK();
