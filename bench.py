@@ -33,7 +33,10 @@ sys.path.insert(0, ROOT)
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE captured launch of the dominant kernel
 # (ncu --set full, profiles/r01_ncu_summary_v2.md): fused_pass_kernel at step i=1500 of n=16384
 # (algorithmic single-read bytes of that launch: 8*(16384-1500)*(16384-1501) = 1.772e9)
-NCU_TRAFFIC = {16384: None, 4096: None}
+NCU_TRAFFIC = {16384: 1.784272e9 + 9.264e6, 4096: 77.358e6 + 4.9e6}
+NCU_TRAFFIC_NOTE = ("dram__bytes_read.sum + dram__bytes_write.sum of ONE fused_pass_kernel launch (ncu --set full): "
+                    "n=16384 step 1500 (single-read algorithmic bytes of that launch 1.772e9), "
+                    "n=4096 step 1000 (76.7e6); profiles/r01_ncu_summary_v2.md")
 METRIC = "svd_gpu seconds"
 UNIT = "s"
 
@@ -322,7 +325,7 @@ def run_own(args):
                 "kernel": ("fused_pass_kernel (single-read pass; gemvT/gemvN below 1024 rows) + finish_xf + panel GEMM"
                            if fused_on else "gemvT_kernel + gemvN_kernel + finish_y/x + panel GEMM"),
                 "achieved": ach_survey, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach_survey / pk["hbm_gbs"],
-                "traffic": NCU_TRAFFIC.get(n),
+                "traffic": NCU_TRAFFIC.get(n), "traffic_note": NCU_TRAFFIC_NOTE,
                 "definition": "achieved = SURVEY 8(d) B_alg (12*S bytes: unblocked 3-transfer scheme) / bidiag phase "
                               "time from CUDA events (all bidiag launches); can exceed 1.0 because the panel-deferred "
                               "fused scheme moves fewer bytes than B_alg assumes - see own_scheme_*",
