@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE captured launch of the dominant kernel
 # (ncu --set full, profiles/r01_ncu_summary_v2.md): fused_pass_kernel at step i=1500 of n=16384
 # (algorithmic single-read bytes of that launch: 8*(16384-1500)*(16384-1501) = 1.772e9)
-NCU_TRAFFIC = {16384: 1.784272e9 + 9.264e6, 4096: 77.358e6 + 4.9e6}
+NCU_TRAFFIC = {16384: 1.784272e9 + 9.264e6, 4096: 77.358e6 + 2.543e6}
 NCU_TRAFFIC_NOTE = ("dram__bytes_read.sum + dram__bytes_write.sum of ONE fused_pass_kernel launch (ncu --set full): "
                     "n=16384 step 1500 (single-read algorithmic bytes of that launch 1.772e9), "
                     "n=4096 step 1000 (76.7e6); profiles/r01_ncu_summary_v2.md")
@@ -53,13 +53,13 @@ def bidiag_bytes(m, n, nb, fused=True):
     Per step: the fused pass reads the trailing block (m-i) x (n-i-1) once; the split passes read
     it twice ((m-i)(n-i-1) for the column dots, (m-i-1)(n-i-1) for the row dots); plus one read+write
     of the trailing block per panel for the deferred rank-2nb update.  The fused pass is used while
-    the trailing block has >= 1024 rows and >= 64 columns (bidiag.cu:plan_fused).  Also returns the
+    the trailing block has >= 128 rows and >= 32 columns (bidiag.cu:plan_fused).  Also returns the
     survey's figure 12*S for the unblocked 3-transfer scheme."""
     mn = min(m, n)
     i = np.arange(mn - 1, dtype=np.float64)
     t1 = (m - i) * (n - i - 1)
     t2 = np.where(i < n - 2, (m - i - 1) * (n - i - 1), 0.0)
-    is_fused = (m - i >= 1024) & (n - i - 1 >= 64) & (i < n - 2) if fused else np.zeros_like(i, dtype=bool)
+    is_fused = (m - i >= 128) & (n - i - 1 >= 32) & (i < n - 2) if fused else np.zeros_like(i, dtype=bool)
     reads = np.where(is_fused, t1, t1 + t2).sum()
     ends = np.arange(nb - 1, mn - 1, nb, dtype=np.float64)
     upd = ((m - ends - 1) * (n - ends - 1)).sum()
@@ -322,7 +322,7 @@ def run_own(args):
         ach_survey = b_survey / t_bd / 1e9          # SURVEY.md 8(d) definition: B_alg = 8 * 1.5 * S
         ach_own = b_alg / t_bd / 1e9                # bytes our scheme actually has to move
         roof = {"bound": "hbm",
-                "kernel": ("fused_pass_kernel (single-read pass; gemvT/gemvN below 1024 rows) + finish_xf + panel GEMM"
+                "kernel": ("fused_pass_kernel (single-read pass; gemvT/gemvN below 128 rows) + finish_xf + panel GEMM"
                            if fused_on else "gemvT_kernel + gemvN_kernel + finish_y/x + panel GEMM"),
                 "achieved": ach_survey, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach_survey / pk["hbm_gbs"],
                 "traffic": NCU_TRAFFIC.get(n), "traffic_note": NCU_TRAFFIC_NOTE,

@@ -40,6 +40,8 @@ SIGNATURES = [
     ("svd_gpu_set_option", None, [ctypes.c_char_p, c_int]),
     # include/bidiag_par.h
     ("bidiag_par", None, [c_int, c_int, c_double_p, c_double_p, c_double_p]),
+    ("form_u_par", None, [c_int, c_int, c_double_p, c_double_p]),
+    ("form_v_par", None, [c_int, c_int, c_double_p, c_double_p]),
     ("multU", None, [c_int, c_int, c_int, c_double_p, c_double_p, c_double_p]),
     ("multV", None, [c_int, c_int, c_int, c_double_p, c_double_p, c_double_p]),
     ("svd_gpu_backtransform", None, [c_int, c_int, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
@@ -194,6 +196,17 @@ def backtransform(A_mod, X, Y):
     Xc = np.ascontiguousarray(X, dtype=np.float64)
     Yc = np.ascontiguousarray(Y, dtype=np.float64)
     lib().svd_gpu_backtransform(m, n, _p(Af), _p(Xc), _p(Yc), _p(U), _p(V))
+    return U, V
+
+
+def form_q(A_mod):
+    """form_u_par / form_v_par: explicit Q_L (m x m) and Q_R (n x n) of the bidiagonalization."""
+    Af = _colmajor(A_mod)
+    m, n = Af.shape
+    U = np.zeros((m, m), order="F")
+    V = np.zeros((n, n), order="F")
+    lib().form_u_par(m, n, _p(Af), _p(U))
+    lib().form_v_par(m, n, _p(Af), _p(V))
     return U, V
 
 

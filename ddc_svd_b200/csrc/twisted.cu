@@ -25,6 +25,7 @@
 #include "common.cuh"
 #include "twisted.cuh"
 #include <cfloat>
+#include <cstdlib>
 
 namespace svdgpu {
 
@@ -241,6 +242,56 @@ tw_finalize_kernel(int n, int mb, int ns, const double *__restrict__ a, const do
     }
 }
 
+// ---- left vectors by their own twisted factorization ------------------------------------------
+// For a square upper bidiagonal B, P B^T P (P = index reversal) is again upper bidiagonal, with
+// diagonal a'_j = a_{n-1-j} and super-diagonal b'_j = b_{n-2-j}, and its right singular vectors are
+// the reversed left singular vectors of B.  Running the same qd kernels on (a', b') gives y_i with
+// the accuracy of x_i, whereas y = B x / sigma (parallel-twisted.c:545-549) loses orthogonality
+// like eps * sigma_max / sigma_i.  The pair (x_i, y_i) is oriented by the sign of (B x_i) at the
+// twist position of y_i (its dominant component).
+__global__ void tw_prep_rev_kernel(int n, const double *__restrict__ a, const double *__restrict__ b,
+                                   double *__restrict__ q, double *__restrict__ e, double *__restrict__ ab)
+{
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const double aj = a[n - 1 - j];
+        const double bj = (j < n - 1) ? b[n - 2 - j] : 0.0;
+        q[j] = aj * aj; e[j] = bj * bj; ab[j] = aj * bj;
+    }
+}
+
+__global__ void tw_left_sign_kernel(int n, int ns, const double *__restrict__ a, const double *__restrict__ b,
+                                    const int *__restrict__ kidx, const double *__restrict__ X, long ldx,
+                                    double *__restrict__ sgn)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ns) return;
+    const int r = n - 1 - kidx[t];                         // position of the dominant component of y_t
+    const double *x = X + (size_t)t * ldx;
+    double bx = a[r] * x[r];
+    if (r < n - 1) bx += b[r] * x[r + 1];
+    sgn[t] = (bx < 0.0) ? -1.0 : 1.0;
+}
+
+__global__ void __launch_bounds__(256)
+tw_left_finalize_kernel(int n, int ns, const double *__restrict__ Z, const double *__restrict__ nrm2,
+                        const double *__restrict__ sgn, double *__restrict__ Y, long ldy)
+{
+    __shared__ double tile[32][33];
+    const int t0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+    for (int r = ty; r < 32; r += 8) {
+        const int j = j0 + r, t = t0 + tx;
+        double v = 0.0;
+        if (j < n && t < ns) v = Z[(size_t)j * ns + t] * rsqrt(nrm2[t] + nrm2[ns + t]) * sgn[t];
+        tile[r][tx] = v;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int t = t0 + r, j = j0 + tx;
+        if (t < ns && j < n) Y[(size_t)t * ldy + (n - 1 - j)] = tile[tx][r];
+    }
+}
+
 static int tw_chunk(int mb, int ns)
 {
     const size_t budget = (size_t)4 << 30;                 // bytes for the two scratch panels
@@ -255,7 +306,7 @@ size_t twisted_workspace_bytes(int n, int mb, int ns)
 {
     int c = tw_chunk(mb, ns);
     size_t d = 0;
-    d += 3 * (size_t)mb + 8;            // q, e, ab, pivmin
+    d += 6 * (size_t)mb + 8;            // q, e, ab (+ the reversed set for the left vectors), pivmin
     d += 2 * (size_t)mb * c;            // S, P
     d += 4 * (size_t)c + 8;             // tau, gk, nrm2[2]
     return d * sizeof(double) + (size_t)c * sizeof(int) + 4096;
@@ -271,6 +322,9 @@ void twisted_vectors_device(int n, int mb, const double *a, const double *b, con
     double *q = w;       w += mb;
     double *e = w;       w += mb;
     double *ab = w;      w += mb;
+    double *q2 = w;      w += mb;
+    double *e2 = w;      w += mb;
+    double *ab2 = w;     w += mb;
     double *pivmin = w;  w += 8;
     double *S = w;       w += (size_t)mb * cmax;
     double *P = w;       w += (size_t)mb * cmax;
@@ -281,6 +335,13 @@ void twisted_vectors_device(int n, int mb, const double *a, const double *b, con
 
     tw_prep_kernel<<<1, 1024, 0, st>>>(n, mb, a, b, q, e, ab, pivmin);
     SVD_KERNEL_CHECK();
+    // left vectors from their own twisted factorization when B is square (SVD_GPU_LEFT=bx restores y = Bx/sigma)
+    const char *lenv = getenv("SVD_GPU_LEFT");
+    const bool left_by_twist = (Y != nullptr) && (mb == n) && (n > 1) && !(lenv && lenv[0] == 'b');
+    if (left_by_twist) {
+        tw_prep_rev_kernel<<<ceil_div(n, 256), 256, 0, st>>>(n, a, b, q2, e2, ab2);
+        SVD_KERNEL_CHECK();
+    }
     for (int c0 = 0; c0 < ns; c0 += cmax) {
         const int c = (ns - c0 < cmax) ? ns - c0 : cmax;
         const int gi0 = i0 + c0;
@@ -299,10 +360,24 @@ void twisted_vectors_device(int n, int mb, const double *a, const double *b, con
             }
         }
         dim3 grid(ceil_div(c, 32), ceil_div(mb, 32));
-        tw_finalize_kernel<<<grid, 256, 0, st>>>(n, mb, c, a, b, tau, S, nrm2, X + (size_t)c0 * ldx, ldx,
-                                                 Y ? Y + (size_t)c0 * ldy : nullptr, ldy,
-                                                 sigma_out ? sigma_out + c0 : nullptr);
+        double *Xc = X + (size_t)c0 * ldx;
+        double *Yc = Y ? Y + (size_t)c0 * ldy : nullptr;
+        tw_finalize_kernel<<<grid, 256, 0, st>>>(n, mb, c, a, b, tau, S, nrm2, Xc, ldx, left_by_twist ? nullptr : Yc,
+                                                 ldy, sigma_out ? sigma_out + c0 : nullptr);
         SVD_KERNEL_CHECK();
+        if (left_by_twist) {
+            // y_i from B B^T - sigma_i^2 I (reversed bidiagonal), with the polished sigma_i^2 already in tau
+            tw_qd_kernel<<<dim3(ceil_div(c, 32), 2), 32, 0, st>>>(n, c, q2, e2, tau, pivmin, S, P);
+            SVD_KERNEL_CHECK();
+            tw_select_kernel<<<ceil_div(c, 32), 32 * TWS_SL, 0, st>>>(n, c, tau, S, P, kidx, gk);
+            SVD_KERNEL_CHECK();
+            tw_solve_kernel<<<dim3(ceil_div(c, 32), 2), 32, 0, st>>>(n, c, q2, e2, ab2, pivmin, kidx, S, P, nrm2);
+            SVD_KERNEL_CHECK();
+            tw_left_sign_kernel<<<ceil_div(c, 256), 256, 0, st>>>(n, c, a, b, kidx, Xc, ldx, gk);
+            SVD_KERNEL_CHECK();
+            tw_left_finalize_kernel<<<dim3(ceil_div(c, 32), ceil_div(n, 32)), 256, 0, st>>>(n, c, S, nrm2, gk, Yc, ldy);
+            SVD_KERNEL_CHECK();
+        }
     }
 }
 

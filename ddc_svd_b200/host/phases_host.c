@@ -12,6 +12,8 @@
 #include "../../include/Calculations-Parallel.h"
 #include "../../include/parallel-twisted.h"
 
+static int n_left(int m, int n) { return m < n ? m : n; }
+static int n_right(int m, int n) { return m >= n ? (n >= 2 ? n - 2 : 0) : m; }
 static int env_int(const char *name, int dflt) { const char *e = getenv(name); return e ? atoi(e) : dflt; }
 
 static double *upload_matrix(int m, int n, const double *A, long lda)
@@ -85,9 +87,6 @@ void RighttoLeftSingularVectors(int n, int m, double *A, double *B, double *sigm
     vectors_host(n, m, A, B, sigma, X, Y);
 }
 
-static int n_left(int m, int n) { return m < n ? m : n; }
-static int n_right(int m, int n) { return m >= n ? (n >= 2 ? n - 2 : 0) : m; }
-
 void svd_gpu_backtransform(int m, int n, const double *A_mod, const double *X, const double *Y, double *U,
                            double *V)
 {
@@ -118,6 +117,30 @@ void svd_gpu_backtransform(int m, int n, const double *A_mod, const double *X, c
     }
     svdgpu_free(work); svdgpu_free(dA);
 }
+
+/* Explicit orthogonal factors of the bidiagonalization (bidiag_par.h:33-34, bidiag_par.c:877-988):
+ * U (m x m) = Q_L = H_0 ... H_{mn-1}, V (n x n) = Q_R, from the reflectors stored in A_mod, by
+ * applying the compact-WY panels to the identity on the device. */
+static void form_q(int left, int m, int n, const double *A_mod, double *Qout)
+{
+    const long lda = (m + 1) / 2 * 2;
+    const int rows = left ? m : n;
+    const int nref = left ? n_left(m, n) : n_right(m, n);
+    (void)svdgpu_device_count();
+    double *dA = upload_matrix(m, n, A_mod, lda);
+    double *dC = (double *)svdgpu_malloc(sizeof(double) * (size_t)rows * rows);
+    double *hI = (double *)calloc((size_t)rows * rows, sizeof(double));
+    if (!hI) { fprintf(stderr, "form_q: out of host memory\n"); abort(); }
+    for (int i = 0; i < rows; ++i) hI[i + (size_t)i * rows] = 1.0;
+    svdgpu_h2d(dC, hI, sizeof(double) * (size_t)rows * rows, NULL);
+    void *work = svdgpu_malloc(svdgpu_backtransform_workspace(rows, nref, rows));
+    svdgpu_wy_apply(left, rows, nref, dA, lda, dC, rows, rows, work, NULL);
+    svdgpu_d2h(Qout, dC, sizeof(double) * (size_t)rows * rows, NULL);
+    svdgpu_stream_sync(NULL);
+    svdgpu_free(work); svdgpu_free(dC); svdgpu_free(dA); free(hI);
+}
+void form_u_par(int m, int n, const double *A_mod, double *U) { form_q(1, m, n, A_mod, U); }
+void form_v_par(int m, int n, const double *A_mod, double *V) { form_q(0, m, n, A_mod, V); }
 
 void multU(int m, int n, int vecnum, double *A_mod, double *Y, double *U)
 {

@@ -9,6 +9,10 @@ extern "C" {
 /* A m x n column-major (ld m) is overwritten with the reflectors; alpha[min(m,n)];
  * beta[n-1] if m >= n else beta[m]   (bidiag_par.c:34-450) */
 void bidiag_par(int m, int n, double *A, double *alpha, double *beta);
+/* explicit orthogonal factors, reference signatures (bidiag_par.h:33-34, bidiag_par.c:877-988):
+ * U (m x m, ld m) = Q_L, V (n x n, ld n) = Q_R with A = Q_L B Q_R^T */
+void form_u_par(int m, int n, const double *A_mod, double *U);
+void form_v_par(int m, int n, const double *A_mod, double *V);
 /* one back-transformed vector, reference calling convention (bidiag_par.c:990-1095).
  * multV takes the TRANSPOSED reflector matrix (n x m, ld n) like the reference's caller
  * passes (svd_gpu.c:103,120).  Per-vector calls re-upload the reflectors every time; use

@@ -540,6 +540,42 @@ void orc_apply_right(int m, int n, int vec, const double *AT, const double *X, d
     }
 }
 
+/* explicit orthogonal factors (bidiag.c:252-359 form_u / form_v == bidiag_par.c:877-988):
+ * column i of U is Q_L e_i, column i of V is Q_R e_i, reflectors applied last to first;
+ * reflectors with an index above i leave e_i unchanged, so they are skipped as in the reference */
+void orc_form_u(int m, int n, const double *A_mod, double *U)
+{
+    const int mn = (m < n) ? m : n;
+    for (int i = 0; i < m; ++i) {
+        double *u = U + (size_t)i * m;
+        for (int r = 0; r < m; ++r) u[r] = 0;
+        u[i] = 1;
+        for (int j = (i < mn - 1 ? i : mn - 1); j >= 0; --j) {
+            const double *v = A_mod + j + (size_t)j * m;
+            double ip = 0.0;
+            for (int k = 0; k < m - j; ++k) ip += u[j + k] * v[k];
+            for (int k = j; k < m; ++k) u[k] -= 2 * A_mod[k + (size_t)j * m] * ip;
+        }
+    }
+}
+
+void orc_form_v(int m, int n, const double *A_mod, double *V)
+{
+    const int mn = (m < n) ? m : n;
+    const int nref = (m < n) ? mn : mn - 1;
+    for (int i = 0; i < n; ++i) {
+        double *v = V + (size_t)i * n;
+        for (int r = 0; r < n; ++r) v[r] = 0;
+        v[i] = 1;
+        for (int j = (i < nref ? i - 1 : nref - 1); j >= 0; --j) {
+            const double *row = A_mod + j + (size_t)(j + 1) * m;      /* row reflector j, stride m */
+            double ip = 0.0;
+            for (int k = 0; k < n - j - 1; ++k) ip += row[(size_t)k * m] * v[j + 1 + k];
+            for (int k = j + 1; k < n; ++k) v[k] -= 2 * A_mod[j + (size_t)k * m] * ip;
+        }
+    }
+}
+
 /* ------------------------------------------------------ the whole path */
 
 static double g_t[6];

@@ -49,6 +49,11 @@ void orc_apply_left(int m, int n, int vec, const double *A_mod, const double *Y,
  * AT is the n x m transpose of A_mod (matrix_helper.c:166-174). */
 void orc_apply_right(int m, int n, int vec, const double *AT, const double *X, double *out);
 
+/* bidiag.c:252-359 (form_u, form_v; same results as bidiag_par.c:877-988 form_u_par/form_v_par):
+ * U (m x m) = Q_L, V (n x n) = Q_R from the stored reflectors. */
+void orc_form_u(int m, int n, const double *A_mod, double *U);
+void orc_form_v(int m, int n, const double *A_mod, double *V);
+
 /* svd_gpu.c:53-131. sigma ascending; first min(m,n) columns of U (ld m) and V (ld n). */
 void orc_svd(int m, int n, double *A, double *sigma, double *U, double *V);
 

@@ -273,6 +273,19 @@ def test_backtransform_vs_oracle(D, shape):
         assert np.abs(V[:, i] - v).max() <= 1e-12 * max(1.0, np.abs(v).max())
 
 
+@pytest.mark.parametrize("shape", [(40, 40), (150, 90), (90, 150), (300, 300)])
+def test_form_u_v_vs_oracle(D, shape):
+    # form_u_par / form_v_par (bidiag_par.c:877-988) on the same WY kernels
+    m, n = shape
+    A = util.rand_matrix(m, n, 1.0, 2.0, 4)
+    Am, al, be = util.oracle_bidiag(A)
+    U, V = D.form_q(Am)
+    U_o = np.zeros((m, m), order="F"); V_o = np.zeros((n, n), order="F")
+    util.oracle().orc_form_u(m, n, util.p(Am), util.p(U_o)); util.oracle().orc_form_v(m, n, util.p(Am), util.p(V_o))
+    assert np.abs(U - U_o).max() <= 1e-12 and np.abs(V - V_o).max() <= 1e-12
+    assert np.linalg.norm(U.T @ U - np.eye(m)) <= 100 * EPS * m
+
+
 def test_multU_multV_reference_signatures(D):
     # one vector at a time, with the reference's calling convention (multV takes the transpose)
     L = D.lib()
@@ -363,6 +376,22 @@ def test_svd_gpu_scaling_and_structured_inputs(D):
         sv = np.linalg.svd(A, compute_uv=False)[::-1]
         assert np.abs(sigma - sv).max() <= 10 * EPS * n * sv.max()
         assert np.linalg.norm(A - (U * sigma) @ V.T) <= 100 * EPS * n * np.linalg.norm(A)
+
+
+def test_svd_gpu_graded_spectrum_keeps_U_orthogonal(D):
+    # singular values spread over 12 decades: y = B x / sigma (parallel-twisted.c:545-549) would lose the
+    # orthogonality of U like eps * sigma_max / sigma_i; the left vectors come from their own twisted
+    # factorization of B B^T instead
+    rng = np.random.default_rng(0)
+    n = 300
+    Q1, _ = np.linalg.qr(rng.standard_normal((n, n))); Q2, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    sv = np.logspace(0, -12, n)
+    A = (Q1 * sv) @ Q2.T
+    sigma, U, V, _ = D.svd_gpu(A)
+    c = 100 * EPS * n
+    assert np.abs(sigma - sv[::-1]).max() <= 10 * EPS * n
+    assert np.linalg.norm(U.T @ U - np.eye(n)) <= c and np.linalg.norm(V.T @ V - np.eye(n)) <= c
+    assert np.linalg.norm(A - (U * sigma) @ V.T) / np.linalg.norm(A) <= c
 
 
 # ------------------------------------------------------------------ benchmark sizes: properties

@@ -90,3 +90,22 @@ def test_oracle_rectangular_fixes():
         s, U, V, _ = util.oracle_svd(A)
         met = util.svd_metrics(A, s, U, V)
         assert met["resid"] < 1e-3 and met["sigma_abs_over_max"] < 1e-5
+
+
+@pytest.mark.skipif(util.reference() is None, reason="oracle/_ref not built (no /root/reference)")
+@pytest.mark.parametrize("shape", [(20, 20), (33, 21), (21, 33)])
+def test_oracle_form_uv_vs_reference_build(shape):
+    # explicit Q formation (bidiag.c:252-359): bit-for-bit, and A = U B V^T
+    m, n = shape
+    ref = util.reference()
+    A = util.rand_matrix(m, n, 1.0, 2.0, 4)
+    Am, al, be = util.oracle_bidiag(A)
+    U_o = np.zeros((m, m), order="F"); V_o = np.zeros((n, n), order="F")
+    U_r = np.zeros((m, m), order="F"); V_r = np.zeros((n, n), order="F")
+    util.oracle().orc_form_u(m, n, p(Am), p(U_o)); util.oracle().orc_form_v(m, n, p(Am), p(V_o))
+    ref.form_u(m, n, p(Am), p(U_r)); ref.form_v(m, n, p(Am), p(V_r))
+    assert np.array_equal(U_o, U_r) and np.array_equal(V_o, V_r)
+    B = np.zeros((m, n)); k = min(m, n)
+    B[np.arange(k), np.arange(k)] = al
+    B[np.arange(len(be)), np.arange(len(be)) + 1] = be
+    assert np.abs(U_o @ B @ V_o.T - A).max() < 1e-12

@@ -35,6 +35,8 @@ def oracle():
         L.orc_left_vectors.argtypes = [ctypes.c_int, ctypes.c_int, P, P, P, P, P]
         L.orc_apply_left.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, P, P, P]
         L.orc_apply_right.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, P, P, P]
+        L.orc_form_u.argtypes = [ctypes.c_int, ctypes.c_int, P, P]
+        L.orc_form_v.argtypes = [ctypes.c_int, ctypes.c_int, P, P]
         L.orc_svd.argtypes = [ctypes.c_int, ctypes.c_int, P, P, P, P]
         L.orc_last_timings.argtypes = [P]
         _oracle = L
