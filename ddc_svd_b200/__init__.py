@@ -96,6 +96,8 @@ SIGNATURES = [
     ("svdgpu_twisted_vectors", None, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                       c_long, c_void_p, c_long, c_void_p, c_int, c_void_p, c_void_p]),
     ("svdgpu_backtransform_workspace", c_size_t, [c_int, c_int, c_int]),
+    ("svdgpu_qr_workspace", c_size_t, [c_int, c_int]),
+    ("svdgpu_qr", None, [c_int, c_int, c_void_p, c_long, c_void_p, c_long, c_void_p, c_void_p]),
     ("svdgpu_wy_apply", None, [c_int, c_int, c_int, c_void_p, c_long, c_void_p, c_long, c_int, c_void_p, c_void_p]),
     ("svdgpu_dgemm", None, [c_int, c_int, c_int, c_int, c_int, c_double, c_void_p, c_long, c_void_p, c_long,
                             c_double, c_void_p, c_long, c_void_p]),
@@ -208,6 +210,37 @@ def form_q(A_mod):
     lib().form_u_par(m, n, _p(Af), _p(U))
     lib().form_v_par(m, n, _p(Af), _p(V))
     return U, V
+
+
+def qr_tall(A):
+    """Householder QR used by the QR-first route of svd_gpu() for m >> n (include/cuda-helper.h,
+    svdgpu_qr): returns (A_qr, R, Q1) with A_qr the reflector storage, R (n x n) and the thin
+    Q1 = Q [I_n; 0] (m x n) formed through the same compact-WY apply the SVD uses."""
+    L = lib()
+    Af = _colmajor(A)
+    m, n = Af.shape
+    nb = Af.nbytes
+    dA = L.svdgpu_malloc(nb)
+    dR = L.svdgpu_malloc(8 * n * n)
+    dQ = L.svdgpu_malloc(nb)
+    work = L.svdgpu_malloc(max(L.svdgpu_qr_workspace(m, n), L.svdgpu_backtransform_workspace(m, n, n)))
+    try:
+        L.svdgpu_h2d(dA, _p(Af), nb, None)
+        L.svdgpu_qr(m, n, dA, m, dR, n, work, None)
+        Q1 = np.zeros((m, n), order="F")
+        Q1[np.arange(n), np.arange(n)] = 1.0
+        L.svdgpu_h2d(dQ, _p(Q1), nb, None)
+        L.svdgpu_wy_apply(1, m, n, dA, m, dQ, m, n, work, None)
+        A_qr = np.empty((m, n), order="F")
+        R = np.empty((n, n), order="F")
+        L.svdgpu_d2h(_p(A_qr), dA, nb, None)
+        L.svdgpu_d2h(_p(R), dR, 8 * n * n, None)
+        L.svdgpu_d2h(_p(Q1), dQ, nb, None)
+        L.svdgpu_stream_sync(None)
+    finally:
+        for d in (dA, dR, dQ, work):
+            L.svdgpu_free(d)
+    return A_qr, R, Q1
 
 
 def last_phase_ms():

@@ -184,4 +184,276 @@ void wy_apply_device(int left, int rows, int nref, const double *A, long lda, do
     }
 }
 
+
+// =============================================================================================
+// QR first: for m >> n, A = Q R with Householder reflectors in the library's
+// own convention (unit-norm v, H = I - 2 v v^T, stored from the diagonal down), so that the SVD
+// only has to bidiagonalize the n x n factor R and U = Q [U_R; 0] goes through wy_apply_device.
+// Panels of NBW columns: BLAS2 factorization inside the (L2-resident) panel, then one compact-WY
+// update of the trailing columns on the DMMA GEMM:  A2 <- (I - V T^T V^T) A2.
+// =============================================================================================
+constexpr int QR_GRAM_SPLIT = 64;
+constexpr int QR_CHUNK = 512;       // rows per CTA in the column-dot kernel
+
+// partial column dots of panel column i with the later panel columns, and its norm:
+//   part[chunk][jj] = sum_{r in chunk, r >= i} A[r, i] * A[r, i+1+jj]   (jj < nj),  part[chunk][NBW] = sum A[r,i]^2
+__global__ void __launch_bounds__(256)
+qr_coldots_kernel(const double *__restrict__ A, long lda, int m, int i, int nj, double *__restrict__ part,
+                  double *__restrict__ rowi)
+{
+    // row i of the panel is rewritten by one CTA of the apply kernel while the others still need it
+    if (blockIdx.x == 0 && threadIdx.x <= nj)
+        rowi[threadIdx.x < nj ? threadIdx.x : NBW] = A[i + (long)(threadIdx.x < nj ? i + 1 + threadIdx.x : i) * lda];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r0 = i + blockIdx.x * QR_CHUNK, r1 = min(m, r0 + QR_CHUNK);
+    const double *ci = A + (long)i * lda;
+    double *out = part + (long)blockIdx.x * (NBW + 1);
+    for (int jj = warp; jj <= nj; jj += 8) {                 // jj == nj: the norm
+        const double *cj = (jj < nj) ? A + (long)(i + 1 + jj) * lda : ci;
+        double acc = 0.0;
+        for (int r = r0 + lane; r < r1; r += 32) acc += ci[r] * cj[r];
+        acc = warp_sum(acc);
+        if (lane == 0) out[jj < nj ? jj : NBW] = acc;
+    }
+}
+
+// One launch per panel column i: finish the reduction of the dots the previous launch left behind,
+// form reflector i, apply it to the later panel columns (rows >= i), and — on the freshly updated
+// values still in registers — leave the dots of column i+1 with the columns after it for the next
+// launch.   v = (c + s*nu*e_i)*inv in place, alpha[i] = -s*nu, A[r,j] -= v_r y_j, y_j = 2 (t_j + s*nu*A[i,j]) inv.
+// part/rowi are double-buffered by the caller (other CTAs of this launch still read the old ones).
+template <int RPT>
+__global__ void __launch_bounds__(256)
+qr_step_kernel(double *__restrict__ A, long lda, int m, int i, int nj, const double *__restrict__ part, int nchunk,
+               const double *__restrict__ rowi, double *__restrict__ part_out, double *__restrict__ rowi_out,
+               double *__restrict__ alpha)
+{
+    __shared__ double s_y[NBW];
+    __shared__ double s_red[8][NBW];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (t <= nj) {
+        double a2 = 0.0;
+        const int slot = (t < nj) ? t : NBW;
+        for (int c = 0; c < nchunk; ++c) a2 += part[(long)c * (NBW + 1) + slot];
+        s_y[t < nj ? t : NBW - 1] = a2;                      // raw dots; the norm parks in the last slot
+    }
+    __syncthreads();
+    const double ci = rowi[NBW];
+    const double nrm2 = s_y[NBW - 1];
+    const double nu = sqrt(nrm2), sg = (ci < 0.0) ? -1.0 : 1.0, snu = sg * nu;
+    const double sc = sqrt(2.0) * sqrt(nu * nu + fabs(nu * ci));
+    const double inv = (sc > 0.0) ? 1.0 / sc : 0.0;
+    __syncthreads();
+    if (t < nj) s_y[t] = 2.0 * (s_y[t] + snu * rowi[t]) * inv;
+    __syncthreads();
+
+    const int rbase = i + blockIdx.x * (256 * RPT) + t;
+    double v[RPT], n1[RPT];
+    double *col[RPT];
+    bool live[RPT], nxt[RPT];
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+        const int r = rbase + 256 * k;
+        live[k] = r < m;
+        nxt[k] = live[k] && r > i;                           // rows of the next reflector
+        col[k] = A + (live[k] ? r : i) + (long)i * lda;
+        v[k] = live[k] ? (*col[k] + (r == i ? snu : 0.0)) * inv : 0.0;
+        n1[k] = 0.0;
+    }
+    double *po = part_out + (long)blockIdx.x * (NBW + 1);
+    constexpr int JB = 8;                                    // columns loaded ahead of the dependent stores
+    if (nj > 0) {                                            // column i+1: the next reflector's column
+        const double y = s_y[0];
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+            double *pa = col[k] + lda;
+            double a = 0.0;
+            if (live[k]) { a = *pa - v[k] * y; *pa = a; }
+            n1[k] = nxt[k] ? a : 0.0;
+            acc += n1[k] * a;
+            if (rbase + 256 * k == i + 1) rowi_out[NBW] = a;
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) s_red[warp][0] = acc;
+    }
+    for (int j0 = 1; j0 < nj; j0 += JB) {
+        double a[RPT][JB];
+#pragma unroll
+        for (int k = 0; k < RPT; ++k)
+#pragma unroll
+            for (int q = 0; q < JB; ++q)
+                a[k][q] = (live[k] && j0 + q < nj) ? col[k][(long)(j0 + q + 1) * lda] : 0.0;
+#pragma unroll
+        for (int q = 0; q < JB; ++q) {
+            if (j0 + q < nj) {
+                const double y = s_y[j0 + q];
+                double acc = 0.0;
+#pragma unroll
+                for (int k = 0; k < RPT; ++k) {
+                    const double an = a[k][q] - v[k] * y;
+                    if (live[k]) col[k][(long)(j0 + q + 1) * lda] = an;
+                    acc += n1[k] * an;
+                    if (rbase + 256 * k == i + 1) rowi_out[j0 + q - 1] = an;      // row i+1 for the next launch
+                }
+                acc = warp_sum(acc);
+                if (lane == 0) s_red[warp][j0 + q] = acc;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < RPT; ++k)
+        if (live[k]) *col[k] = v[k];
+    __syncthreads();
+    if (t < nj) {
+        double a2 = 0.0;
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) a2 += s_red[w8][t];
+        po[t == 0 ? NBW : t - 1] = a2;                       // jj = 0 is the next column's own norm
+    }
+    if (blockIdx.x == 0 && t == 0) alpha[i] = -snu;
+}
+
+// clean copy of panel p0: Vp[r - p0, jj] = A[r, p0 + jj] for r >= p0 + jj, else 0   ((m - p0) x NBW)
+__global__ void qr_extract_panel_kernel(const double *__restrict__ A, long lda, int m, int n, int p0,
+                                        double *__restrict__ Vp, long ldv)
+{
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long rows = m - p0;
+    if (idx >= rows * NBW) return;
+    const int rr = (int)(idx % rows), jj = (int)(idx / rows);
+    double v = 0.0;
+    if (p0 + jj < n && rr >= jj) v = A[(p0 + rr) + (long)(p0 + jj) * lda];
+    Vp[rr + (long)jj * ldv] = v;
+}
+
+// R (n x n, ldr): strict upper triangle from A, diagonal from alpha, zero below
+__global__ void qr_copy_r_kernel(const double *__restrict__ A, long lda, const double *__restrict__ alpha, int n,
+                                 double *__restrict__ R, long ldr)
+{
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)ldr * n) return;
+    const int r = (int)(idx % ldr), c = (int)(idx / ldr);
+    double v = 0.0;
+    if (r < n) v = (r < c) ? A[r + (long)c * lda] : (r == c ? alpha[c] : 0.0);
+    R[r + (long)c * ldr] = v;
+}
+
+size_t qr_workspace_bytes(int m, int n)
+{
+    const long ldv = round_up(m, 2);
+    size_t d = 0;
+    d += 2 * (size_t)ldv * NBW;                          // Vp, Vp T^T
+    d += 2 * (size_t)NBW * NBW;                          // G, T
+    d += (size_t)NBW * n;                                // W
+    d += (size_t)WY_MAX_SPLIT * NBW * n;                 // split-K partials of W
+    d += 2 * (size_t)(ceil_div(m, 256) + 1) * (NBW + 1); // column-dot partials + stashed row, double-buffered
+    d += (size_t)QR_GRAM_SPLIT * NBW * NBW;              // split-K partials of the Gram matrix
+    d += (size_t)n + 8;                                  // alpha
+    return d * sizeof(double) + 4096;
+}
+
+// A (m x n, m >= n) <- reflectors (from the diagonal down) and, above the diagonal, R's strict upper
+// triangle; R (n x n, ldr) receives the full triangular factor.
+void qr_device(int m, int n, double *A, long lda, double *R, long ldr, void *workspace, cudaStream_t st)
+{
+    const long ldv = round_up(m, 2);
+    double *w = (double *)workspace;
+    double *Vp = w;    w += (size_t)ldv * NBW;
+    double *VTt = w;   w += (size_t)ldv * NBW;
+    double *G = w;     w += (size_t)NBW * NBW;
+    double *T = w;     w += (size_t)NBW * NBW;
+    double *W = w;     w += (size_t)NBW * n;
+    double *Wp = w;    w += (size_t)WY_MAX_SPLIT * NBW * n;
+    const size_t pstride = (size_t)(ceil_div(m, 256) + 1) * (NBW + 1);
+    double *partb[2], *rowib[2];
+    partb[0] = w; rowib[0] = w + pstride - (NBW + 1); w += pstride;
+    partb[1] = w; rowib[1] = w + pstride - (NBW + 1); w += pstride;
+    double *Gp = w;    w += (size_t)QR_GRAM_SPLIT * NBW * NBW;
+    double *alpha = w;
+    int dev = 0, nsm = 148;
+    SVD_CUDA_CHECK(cudaGetDevice(&dev));
+    SVD_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    const int tsmem = NBW * (NBW + 1) * (int)sizeof(double);
+    SVD_CUDA_CHECK(cudaFuncSetAttribute(wy_tinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tsmem));
+
+    for (int p0 = 0; p0 < n; p0 += NBW) {
+        const int pw = (n - p0 < NBW) ? n - p0 : NBW;
+        // ---- panel factorization (BLAS2, panel resident in L2): one launch per column
+        {
+            const int nj0 = pw - 1, L0 = m - p0;
+            qr_coldots_kernel<<<ceil_div(L0, QR_CHUNK), 256, 0, st>>>(A, lda, m, p0, nj0, partb[0], rowib[0]);
+            SVD_KERNEL_CHECK();
+            int nchunk = ceil_div(L0, QR_CHUNK), cur = 0;
+            for (int i = p0; i < p0 + pw; ++i) {
+                const int nj = p0 + pw - i - 1, L = m - i;
+                if (L >= 256 * 2 * nsm / 2) {
+                    const int nb = ceil_div(L, 512);
+                    qr_step_kernel<2><<<nb, 256, 0, st>>>(A, lda, m, i, nj, partb[cur], nchunk, rowib[cur],
+                                                          partb[cur ^ 1], rowib[cur ^ 1], alpha);
+                    nchunk = nb;
+                } else {
+                    const int nb = ceil_div(L, 256);
+                    qr_step_kernel<1><<<nb, 256, 0, st>>>(A, lda, m, i, nj, partb[cur], nchunk, rowib[cur],
+                                                          partb[cur ^ 1], rowib[cur ^ 1], alpha);
+                    nchunk = nb;
+                }
+                SVD_KERNEL_CHECK();
+                cur ^= 1;
+            }
+        }
+        const int ntrail = n - p0 - pw;
+        if (ntrail <= 0) break;
+        // ---- trailing update  A2 <- A2 - (V T^T) (V^T A2),  T = (striu(V^T V) + I/2)^-1
+        const int rows = m - p0;
+        qr_extract_panel_kernel<<<ceil_div((long)rows * NBW, 256), 256, 0, st>>>(A, lda, m, n, p0, Vp, ldv);
+        SVD_KERNEL_CHECK();
+        GemmArgs g = {};
+        g.M = NBW; g.N = NBW; g.K = rows; g.A = Vp; g.lda = ldv; g.transA = 1; g.B = Vp; g.ldb = ldv; g.transB = 0;
+        g.alpha = 1.0; g.beta = 0.0; g.batch = 1;
+        int gs = rows / 512;
+        if (gs > QR_GRAM_SPLIT) gs = QR_GRAM_SPLIT;
+        if (gs > 1) {
+            g.C = Gp; g.ldc = NBW; g.splitk = gs; g.sSplit = (long)NBW * NBW;
+            dgemm_dmma(g, st);
+            sum_partials(G, NBW, Gp, NBW, (long)NBW * NBW, gs, NBW, NBW, 1.0, 0.0, st);
+        } else {
+            g.C = G; g.ldc = NBW; g.splitk = 1;
+            dgemm_dmma(g, st);
+        }
+        wy_tinv_kernel<<<1, NBW, tsmem, st>>>(G, T);
+        SVD_KERNEL_CHECK();
+        GemmArgs g2 = {};
+        g2.M = rows; g2.N = NBW; g2.K = NBW; g2.A = Vp; g2.lda = ldv; g2.transA = 0; g2.B = T; g2.ldb = NBW; g2.transB = 1;
+        g2.C = VTt; g2.ldc = ldv; g2.alpha = 1.0; g2.beta = 0.0; g2.batch = 1; g2.splitk = 1;
+        dgemm_dmma(g2, st);
+        double *A2 = A + p0 + (long)(p0 + pw) * lda;
+        int tiles = ceil_div(ntrail, 64), split = 1;
+        if (tiles < 2 * nsm) {
+            split = (2 * nsm) / tiles;
+            int maxs = rows / 256;
+            if (split > maxs) split = maxs;
+            if (split > WY_MAX_SPLIT) split = WY_MAX_SPLIT;
+            if (split < 1) split = 1;
+        }
+        GemmArgs g3 = {};
+        g3.M = NBW; g3.N = ntrail; g3.K = rows; g3.A = Vp; g3.lda = ldv; g3.transA = 1; g3.B = A2; g3.ldb = lda; g3.transB = 0;
+        g3.alpha = 1.0; g3.beta = 0.0; g3.batch = 1;
+        if (split > 1) {
+            g3.C = Wp; g3.ldc = NBW; g3.splitk = split; g3.sSplit = (long)NBW * ntrail;
+            dgemm_dmma(g3, st);
+            sum_partials(W, NBW, Wp, NBW, (long)NBW * ntrail, split, NBW, ntrail, 1.0, 0.0, st);
+        } else {
+            g3.C = W; g3.ldc = NBW; g3.splitk = 1;
+            dgemm_dmma(g3, st);
+        }
+        GemmArgs g4 = {};
+        g4.M = rows; g4.N = ntrail; g4.K = NBW; g4.A = VTt; g4.lda = ldv; g4.transA = 0; g4.B = W; g4.ldb = NBW; g4.transB = 0;
+        g4.C = A2; g4.ldc = lda; g4.alpha = -1.0; g4.beta = 1.0; g4.batch = 1; g4.splitk = 1;
+        dgemm_dmma(g4, st);
+    }
+    qr_copy_r_kernel<<<ceil_div(ldr * n, 256), 256, 0, st>>>(A, lda, alpha, n, R, ldr);
+    SVD_KERNEL_CHECK();
+}
+
 } // namespace svdgpu

@@ -142,6 +142,12 @@ size_t svdgpu_backtransform_workspace(int rows, int nref, int nc)
 {
     return backtransform_workspace_bytes(rows, nref, nc);
 }
+size_t svdgpu_qr_workspace(int m, int n) { return qr_workspace_bytes(m, n); }
+void svdgpu_qr(int m, int n, double *dA, long lda, double *dR, long ldr, void *dwork, void *stream)
+{
+    if (m < n) { fprintf(stderr, "svdgpu_qr: needs m >= n (m=%d n=%d)\n", m, n); abort(); }
+    qr_device(m, n, dA, lda, dR, ldr, dwork, S(stream));
+}
 void svdgpu_wy_apply(int left, int rows, int nref, const double *dA_mod, long lda, double *dC, long ldc,
                      int nc, void *dwork, void *stream)
 {

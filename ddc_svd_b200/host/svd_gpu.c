@@ -23,6 +23,8 @@ typedef struct {
     void *arena;
     size_t arena_bytes;
     int nb, rqi;
+    int qr_first;             /* 1: m >= qr_ratio10/10 * n goes through QR first */
+    int qr_ratio10;
     float ms[7];
     int ms_pending;           /* events recorded but not yet read */
 } svd_ctx;
@@ -44,7 +46,9 @@ static void ctx_init(void)
     const char *e;
     (void)svdgpu_device_count();                 /* aborts loudly when there is no GPU */
     if ((e = getenv("SVD_GPU_DEVICE")) != NULL) svdgpu_set_device(atoi(e));
-    g.nb = 32; g.rqi = 1;
+    g.nb = 32; g.rqi = 1; g.qr_first = 1; g.qr_ratio10 = 25;
+    if ((e = getenv("SVD_GPU_QR_FIRST")) != NULL) g.qr_first = atoi(e);
+    if ((e = getenv("SVD_GPU_QR_RATIO10")) != NULL) g.qr_ratio10 = atoi(e);
     if ((e = getenv("SVD_GPU_NB")) != NULL) g.nb = atoi(e);
     if ((e = getenv("SVD_GPU_RQI")) != NULL) g.rqi = atoi(e);
     g.stream = svdgpu_stream_create();
@@ -59,6 +63,8 @@ void svd_gpu_set_option(const char *name, int value)
     ctx_init();
     if (!strcmp(name, "nb")) g.nb = value;
     else if (!strcmp(name, "rqi")) g.rqi = value;
+    else if (!strcmp(name, "qr_first")) g.qr_first = value;
+    else if (!strcmp(name, "qr_ratio10")) g.qr_ratio10 = value;
     else if (!strcmp(name, "release")) {          /* drop the cached device arena */
         svdgpu_free(g.arena); g.arena = NULL; g.arena_bytes = 0;
     } else { fprintf(stderr, "svd_gpu_set_option: unknown option '%s'\n", name); abort(); }
@@ -90,6 +96,21 @@ static size_t phase_work_bytes(int m, int n, int ns, long lda)
         w = maxz(w, svdgpu_backtransform_workspace(n, n_right(m, n), ns));
     }
     return up256(w);
+}
+
+/* QR first: worthwhile once the m x n bidiagonalization (BLAS2, ~4 m n^2) costs well more than a
+ * tensor-core QR (2 m n^2 on the DMMA GEMM) plus the n x n problem */
+static int use_qr_first(int m, int n)
+{
+    return g.qr_first && n >= 2 && (long)m * 10 >= (long)n * g.qr_ratio10 && m > n;
+}
+static size_t qr_r_bytes(int n) { return up256(sizeof(double) * (size_t)((n + 1) / 2 * 2) * n); }
+static size_t qr_extra_bytes(int m, int n, int ns)
+{
+    if (!use_qr_first(m, n)) return 0;
+    const long ldr = (n + 1) / 2 * 2;
+    return qr_r_bytes(n) + maxz(up256(svdgpu_qr_workspace(m, n)),
+                                maxz(phase_work_bytes(n, n, ns, ldr), phase_work_bytes(m, n, ns, (m + 1) / 2 * 2)));
 }
 
 static void vectors_core(int m, int n, const double *dA, long lda, const double *dalpha, const double *dbeta,
@@ -148,6 +169,34 @@ static void svd_dev_inner(int m, int n, double *dA, long lda, double *dsigma, do
     /* range guard: exact power-of-two scaling when max|A| is far from 1 (sigma is scaled back below) */
     svdgpu_scale_matrix(m, n, dA, lda, dscale, (double *)work, stream);
     svdgpu_memset(dbeta, 0, sizeof(double) * ((size_t)mn + 1), stream);
+    if (use_qr_first(m, n)) {
+        /* A = Q R, then the square problem on R; dA keeps Q's reflectors (and R above the diagonal),
+         * not bidiagonalization reflectors */
+        const long ldr = (n + 1) / 2 * 2;
+        double *dR = (double *)work;
+        work = (char *)work + qr_r_bytes(n);
+        svdgpu_qr(m, n, dA, lda, dR, ldr, work, stream);
+        svdgpu_bidiag(n, n, dR, ldr, dalpha, dbeta, work, g.nb, stream);
+        svdgpu_event_record(g.ev[1], stream);
+        if (ev_after_bidiag_for_copy) svdgpu_event_record(ev_after_bidiag_for_copy, stream);
+        svdgpu_ddc_values(n, dalpha, dbeta, want_vec ? dsig : dsigma, work, stream);
+        svdgpu_event_record(g.ev[2], stream);
+        if (want_vec) {
+            svdgpu_memset(dU, 0, sizeof(double) * (size_t)ldu * n, stream);
+            svdgpu_memset(dV, 0, sizeof(double) * (size_t)ldv * n, stream);
+            svdgpu_twisted_vectors(n, n, dalpha, dbeta, dsig, n, 0, n, dV, ldv, dU, ldu, dsigma, g.rqi, work, stream);
+            svdgpu_event_record(g.ev[3], stream);
+            svdgpu_wy_apply(1, n, n_left(n, n), dR, ldr, dU, ldu, n, work, stream);
+            svdgpu_wy_apply(0, n, n_right(n, n), dR, ldr, dV, ldv, n, work, stream);
+            svdgpu_wy_apply(1, m, n, dA, lda, dU, ldu, n, work, stream);      /* U = Q [U_R; 0] */
+        } else {
+            svdgpu_event_record(g.ev[3], stream);
+        }
+        svdgpu_scale_vector(mn, dsigma, dscale + 1, stream);
+        svdgpu_event_record(g.ev[4], stream);
+        g.ms_pending = 1;
+        return;
+    }
     svdgpu_bidiag(m, n, dA, lda, dalpha, dbeta, work, g.nb, stream);
     svdgpu_event_record(g.ev[1], stream);
     if (ev_after_bidiag_for_copy) svdgpu_event_record(ev_after_bidiag_for_copy, stream);
@@ -174,7 +223,7 @@ void svd_gpu_dev(int m, int n, double *dA, long lda, double *dsigma, double *dU,
     ctx_init();
     const int mn = m < n ? m : n;
     const int ns = (dU && dV) ? mn : 0;
-    char *scratch = arena_get(small_bytes(mn) + phase_work_bytes(m, n, ns, lda));
+    char *scratch = arena_get(small_bytes(mn) + maxz(phase_work_bytes(m, n, ns, lda), qr_extra_bytes(m, n, ns)));
     g.ms[0] = g.ms[5] = 0.f;
     svd_dev_inner(m, n, dA, lda, dsigma, dU, ldu, dV, ldv, scratch, stream, NULL);
 }
@@ -208,7 +257,8 @@ void svd_gpu(int m, int n, double *A, double *sigma, double *U, double *V)
     const size_t bytesU = want_vec ? up256(sizeof(double) * (size_t)m * mn) : 0;
     const size_t bytesV = want_vec ? up256(sizeof(double) * (size_t)n * mn) : 0;
     char *base = arena_get(bytesA + bytesU + bytesV + up256(sizeof(double) * (size_t)mn) + small_bytes(mn) +
-                           phase_work_bytes(m, n, want_vec ? mn : 0, lda));
+                           maxz(phase_work_bytes(m, n, want_vec ? mn : 0, lda),
+                                qr_extra_bytes(m, n, want_vec ? mn : 0)));
     double *dA = (double *)base;
     double *dU = want_vec ? (double *)(base + bytesA) : NULL;
     double *dV = want_vec ? (double *)(base + bytesA + bytesU) : NULL;

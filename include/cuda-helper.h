@@ -68,6 +68,12 @@ void   svdgpu_twisted_vectors(int n, int mb, const double *da, const double *db,
 size_t svdgpu_backtransform_workspace(int rows, int nref, int nc);
 void   svdgpu_wy_apply(int left, int rows, int nref, const double *dA_mod, long lda, double *dC,
                        long ldc, int nc, void *dwork, void *stream);
+/* Householder QR of a tall matrix (m >= n) in the same reflector convention, used by svd_gpu() for
+ * m >> n (LAPACK dgesdd's "QR first" route; the reference has no counterpart and bidiagonalizes the
+ * full m x n matrix, bidiag_par.c:310-397).  dA <- reflectors (diagonal and below) + strict upper
+ * triangle of R; dR (n x n, ldr) <- R.  svdgpu_wy_apply(1, m, n, dA, ...) then applies Q. */
+size_t svdgpu_qr_workspace(int m, int n);
+void   svdgpu_qr(int m, int n, double *dA, long lda, double *dR, long ldr, void *dwork, void *stream);
 /* FP64 DMMA GEMM building block: C = beta*C + alpha*op(A)*op(B), column-major */
 void   svdgpu_dgemm(int transA, int transB, int M, int N, int K, double alpha, const double *dA,
                     long lda, const double *dB, long ldb, double beta, double *dC, long ldc,

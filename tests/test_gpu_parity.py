@@ -341,6 +341,43 @@ def test_svd_gpu_vs_oracle_512(D):
     assert np.abs(sigma - sv).max() < 1e-3 * np.abs(s_o - sv).max()
 
 
+# ------------------------------------------------------------------ QR first (m >> n)
+@pytest.mark.parametrize("shape", [(5, 2), (300, 100), (1025, 33), (5000, 257), (70000, 130), (4097, 512)])
+def test_qr_tall_vs_lapack(D, shape):
+    m, n = shape
+    A = util.rand_matrix(m, n)
+    A_qr, R, Q1 = D.qr_tall(A)
+    e = EPS * m
+    assert np.all(np.tril(R, -1) == 0.0)
+    assert np.array_equal(np.triu(A_qr[:n], 1), np.triu(R, 1))         # R's strict upper triangle stays in place
+    assert np.linalg.norm(Q1.T @ Q1 - np.eye(n)) <= 100 * e
+    assert np.linalg.norm(Q1 @ R - A) / np.linalg.norm(A) <= 100 * e
+    # R is unique up to row signs: same as LAPACK's
+    R_l = np.linalg.qr(A, mode="r")
+    sg = np.sign(np.diag(R)) * np.sign(np.diag(R_l))
+    assert np.abs(R - sg[:, None] * R_l).max() <= 1000 * e * np.abs(R_l).max()
+    # unit-norm reflectors from the diagonal down (the library's convention, bidiag_par.c:92-131)
+    for j in (0, n // 2, n - 1):
+        assert abs(np.linalg.norm(A_qr[j:, j]) - 1.0) <= 1e-13
+
+
+@pytest.mark.parametrize("shape", [(1025, 33), (4000, 300), (20000, 512), (9001, 1000), (40, 2), (7, 3)])
+def test_svd_gpu_qr_first_route(D, shape):
+    m, n = shape
+    A = util.rand_matrix(m, n)
+    D.set_option("qr_first", 0)
+    try:
+        s0, U0, V0, _ = D.svd_gpu(A)
+    finally:
+        D.set_option("qr_first", 1)
+    s1, U1, V1, _ = D.svd_gpu(A)
+    check_lapack_bounds(A, s1, U1, V1)
+    check_lapack_bounds(A, s0, U0, V0)
+    assert np.abs(s1 - s0).max() <= 10 * EPS * m * s0.max()
+    s2, _, _, _ = D.svd_gpu(A, vectors=False)
+    assert np.abs(s2 - s1).max() <= 10 * EPS * m * s1.max()
+
+
 def test_svd_gpu_values_only(D):
     A = util.rand_matrix(300, 300)
     s1, _, _, _ = D.svd_gpu(A, vectors=False)
