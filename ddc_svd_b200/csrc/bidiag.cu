@@ -442,6 +442,9 @@ finish_xf_kernel(double *__restrict__ A, long lda, int i, int m, int n, int k, i
     const int R = n - i - 1, Lb = m - i - 1;
     const bool rowblk = (int)blockIdx.x < nRowBlk;
     constexpr int ZV = NBMAX / XF_SL + 1, ZX = NBMAX / XF_SL;       // 3, 2
+    // programmatic dependent launch: started while the fused pass drains; its results are read below
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     // ---- loads that depend on nothing: first row group, the row of Q, r_first
     int idx = blockIdx.x * (32 * RB) + lane;
@@ -715,6 +718,7 @@ static FusedPlan plan_fused(int i, int m, int n, int mpad, int nsm, int min_rows
     return p;
 }
 
+static bool g_pdl = true;       // SVD_GPU_PDL=0 turns programmatic dependent launch off
 template <int RPT> static void launch_fused_t(const FusedArgs &fa, const FusedPlan &pl, cudaStream_t st)
 {
     cudaLaunchConfig_t cfg = {};
@@ -722,12 +726,28 @@ template <int RPT> static void launch_fused_t(const FusedArgs &fa, const FusedPl
     cfg.blockDim = dim3(FZ_THREADS);
     cfg.dynamicSmemBytes = FZ_SMEM_BYTES;
     cfg.stream = st;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = pl.CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = g_pdl ? 2 : 1;
     SVD_CUDA_CHECK(cudaLaunchKernelEx(&cfg, fused_pass_kernel<RPT>, fa));
     SVD_KERNEL_CHECK();
+}
+// finish_xf as the programmatic dependent of the fused pass
+template <int RB, typename... Args> static void launch_finish_xf(int grid, cudaStream_t st, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(1024);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = g_pdl ? 1 : 0;
+    SVD_CUDA_CHECK(cudaLaunchKernelEx(&cfg, finish_xf_kernel<RB>, args...));
 }
 static void launch_fused(const FusedArgs &fa, const FusedPlan &pl, cudaStream_t st)
 {
@@ -761,6 +781,7 @@ void bidiag_device(int m, int n, double *A, long lda, double *alpha, double *bet
     // measurement (profiles/): the split passes unless the fused pass is faster at this size
     const char *fenv = getenv("SVD_GPU_FUSED");
     const bool use_fused = (fenv != nullptr) ? (fenv[0] != '0') : FZ_DEFAULT_ON;
+    { const char *pe = getenv("SVD_GPU_PDL"); g_pdl = pe ? (pe[0] != '0') : true; }
     if (use_fused) fused_set_attributes();
     // thresholds below which the split passes are used (overridable for tests)
     const char *e1 = getenv("SVD_GPU_FUSED_MIN_ROWS"), *e2 = getenv("SVD_GPU_FUSED_MIN_COLS");
@@ -798,18 +819,19 @@ void bidiag_device(int m, int n, double *A, long lda, double *alpha, double *bet
             fa.tmpN = b.tmpN; fa.ldt = lda;
             fa.dots1 = dots1_ready ? b.dots1p : b.dots1; fa.nparts1 = dots1_ready ? dots1_parts : 0;
             fa.dots2p = b.dots2p; fa.alpha = alpha; fa.T = pl.T; fa.NC = pl.NC; fa.Lc = pl.Lc;
+            fa.prefetch = (g_pdl && dots1_ready && k > 0) ? 1 : 0;   // predecessor is finish_xf (not the panel GEMM)
             launch_fused(fa, pl, st);
             if (Lb > 4096) {
                 const int nRowBlk = ceil_div(Lb, 128), nColBlk = ceil_div(R, 1024);
-                finish_xf_kernel<4><<<nRowBlk + nColBlk, 1024, 0, st>>>(A, lda, i, m, n, k, nb, b.P, b.ldp, b.Q, b.ldq,
-                                                                        b.c, b.rv, b.tmpN, lda, pl.NC, b.dots2p, pl.NC,
-                                                                        beta, nRowBlk, b.dots1p);
+                launch_finish_xf<4>(nRowBlk + nColBlk, st, A, lda, i, m, n, k, nb, b.P, b.ldp, b.Q, b.ldq, b.c,
+                                    (const double *)b.rv, (const double *)b.tmpN, lda, pl.NC,
+                                    (const double *)b.dots2p, pl.NC, beta, nRowBlk, b.dots1p);
                 dots1_parts = nRowBlk;
             } else {
                 const int nRowBlk = ceil_div(Lb, 32), nColBlk = ceil_div(R, 1024);
-                finish_xf_kernel<1><<<nRowBlk + nColBlk, 1024, 0, st>>>(A, lda, i, m, n, k, nb, b.P, b.ldp, b.Q, b.ldq,
-                                                                        b.c, b.rv, b.tmpN, lda, pl.NC, b.dots2p, pl.NC,
-                                                                        beta, nRowBlk, b.dots1p);
+                launch_finish_xf<1>(nRowBlk + nColBlk, st, A, lda, i, m, n, k, nb, b.P, b.ldp, b.Q, b.ldq, b.c,
+                                    (const double *)b.rv, (const double *)b.tmpN, lda, pl.NC,
+                                    (const double *)b.dots2p, pl.NC, beta, nRowBlk, b.dots1p);
                 dots1_parts = nRowBlk;
             }
             SVD_KERNEL_CHECK();

@@ -74,6 +74,8 @@ struct FusedArgs {
     double *dots2p;               // [cluster][2*NBMAX+2] partials of [Y^T r | U^T r | r.r] for finish_xf
     double *alpha;
     int T, NC, Lc;                // column tiles, clusters, rows per CTA (even)
+    int prefetch;                 // 1: the preceding kernel does not write the trailing matrix, so the first
+                                  //    tiles may be fetched before griddepcontrol.wait (programmatic dependent launch)
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------
@@ -209,11 +211,37 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
         for (int x = 0; x < FZ_XR; ++x) fz_mbar_init(xbar + x, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // ---- programmatic dependent launch: this grid may start while its predecessor (finish_xf of the
+    //      previous step) drains.  The trailing matrix is not written by that kernel, so the producer
+    //      fills the pipeline first; everything the predecessor produces is read after the wait.
+    const int ntiles = (a.T > g) ? (a.T - g + NC - 1) / NC : 0;
+    int npre = 0;
+    if (a.prefetch) {
+        npre = ntiles < FZ_STAGES ? ntiles : FZ_STAGES;
+        if (tid == 0) {
+            for (int nt = 0; nt < npre; ++nt) {
+                const int j0 = i + 1 + (g + nt * NC) * CBW;
+                int ncols = a.n - j0;
+                if (ncols > CBW) ncols = CBW;
+                const unsigned bytes = (unsigned)ncols * (unsigned)len * 8u;
+                if (bytes) {
+                    fz_mbar_arrive_expect_tx(full + nt, bytes);
+                    for (int q = 0; q < ncols; ++q)
+                        fz_bulk_g2s(tile + (size_t)nt * FZ_STAGE + (size_t)q * Lc, a.A + rs + (long)(j0 + q) * a.lda,
+                                    (unsigned)len * 8u, full + nt);
+                } else {
+                    fz_mbar_arrive(full + nt);
+                }
+            }
+        }
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // ---- combine the partial dots of the current column c (left by finish_xf) in a fixed order;
-    //      the tile area is still unused and serves as scratch
+    //      the panel-row area is still unused and serves as scratch (the tiles may already be in flight)
     {
         constexpr int S1 = 2 * NBMAX + 2;
-        double *s_part = tile, *s_d1 = tile + 5 * S1;
+        double *s_part = qrow, *s_d1 = qrow + 5 * S1;
         const int ne = 2 * k + 1;                         // [0..k) V^T c, [nb..nb+k) X^T c, [2nb] c.c
         if (a.nparts1 > 0) {
             const int e = tid / 5, part = tid - 5 * e;    // 5 threads per entry (672/5 = 134 >= 129)
@@ -252,12 +280,11 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
     const double snu = s_sc[0], inv = s_sc[1], vi = s_sc[2];
     if (CS > 1) fz_cluster_sync();                         // barriers exist everywhere before remote traffic
 
-    const int ntiles = (a.T > g) ? (a.T - g + NC - 1) / NC : 0;
     constexpr int S2 = 2 * NBMAX + 2;
 
     if (warp == 0) {
         // ============================ TMA producer warp ============================
-        for (int nt = 0; nt < ntiles; ++nt) {
+        for (int nt = npre; nt < ntiles; ++nt) {
             const int s = nt % FZ_STAGES;
             fz_mbar_wait(empty + s, ((nt / FZ_STAGES) & 1) ^ 1);
             if (lane == 0) {
