@@ -696,25 +696,39 @@ static int sm_targets(int &targetT, int &targetN)
 
 // ---- fused pass launch (cluster launch, TMA/mbarrier kernel of bidiag_fused.cuh) ---------------
 struct FusedPlan { bool ok; int CS, RPT, Lc, T, NC; };
+static int g_max_clusters[3][FZ_MAXCS + 1];   // [RPT index][cluster size]: co-resident clusters (occupancy API)
+static int force_cs = 0;
 static FusedPlan plan_fused(int i, int m, int n, int mpad, int nsm, int min_rows, int min_cols)
 {
     FusedPlan p = {false, 1, 4, 0, 0, 0};
     const int L = m - i, R = n - i - 1;
     if (L < min_rows || R < min_cols) return p;
     const int Ltot = mpad - (i & ~1);
-    int CS = 1;
-    while (CS <= FZ_MAXCS && round_up(ceil_div(Ltot, CS), 2) > FZ_STAGE) CS *= 2;
-    if (CS > FZ_MAXCS) return p;
-    p.CS = CS;
-    p.Lc = (int)round_up(ceil_div(Ltot, CS), 2);
-    p.RPT = 2;                                   // row pairs per sweep thread: rows per CTA <= 512*RPT
-    while (512 * p.RPT < p.Lc) p.RPT *= 2;
-    const int cbw = 8 / p.RPT;
-    p.T = ceil_div(R, cbw);
-    int maxc = nsm / CS;
-    if (maxc > FZ_MAX_CLUSTERS) maxc = FZ_MAX_CLUSTERS;
-    p.NC = p.T < maxc ? p.T : maxc;
-    p.ok = (p.NC >= 1);
+    // Cluster size: the smallest one whose row slice fits a stage is not always the best.  Clusters
+    // are placed inside one GPC, so only g_max_clusters[..][CS] of them are co-resident (measured by
+    // the occupancy API, e.g. fewer than 148/4 for CS = 4); a grid with more clusters than that runs
+    // in two waves.  Among the sizes whose row slice fits a stage pick the one that keeps the most SMs busy.
+    double best = -1.0;
+    for (int CS = 1; CS <= FZ_MAXCS; ++CS) {
+        const int Lc = (int)round_up(ceil_div(Ltot, CS), 2);
+        if (Lc > FZ_STAGE) continue;
+        if (force_cs > 0 && CS != force_cs) continue;
+        int RPT = 2, ri = 0;
+        while (512 * RPT < Lc) { RPT *= 2; ++ri; }
+        const int cbw = 8 / RPT;
+        const int T = ceil_div(R, cbw);
+        int maxc = g_max_clusters[ri][CS];
+        if (maxc <= 0) continue;
+        if (maxc > FZ_MAX_CLUSTERS) maxc = FZ_MAX_CLUSTERS;
+        const int NC = T < maxc ? T : maxc;
+        // SMs kept streaming; ties go to the smaller cluster (shorter exchange, larger tiles)
+        const double score = (double)NC * CS - 1e-3 * CS;
+        if (score > best) {
+            best = score;
+            p.CS = CS; p.Lc = Lc; p.RPT = RPT; p.T = T; p.NC = NC;
+        }
+    }
+    p.ok = (best > 0.0 && p.NC >= 1);
     return p;
 }
 
@@ -757,11 +771,40 @@ static void launch_fused(const FusedArgs &fa, const FusedPlan &pl, cudaStream_t 
     default: launch_fused_t<8>(fa, pl, st); break;
     }
 }
+template <int RPT> static void query_clusters_t(int ri)
+{
+    for (int CS = 1; CS <= FZ_MAXCS; ++CS) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(CS * 148);
+        cfg.blockDim = dim3(FZ_THREADS);
+        cfg.dynamicSmemBytes = FZ_SMEM_BYTES;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int nc = 0;
+        if (cudaOccupancyMaxActiveClusters(&nc, fused_pass_kernel<RPT>, &cfg) != cudaSuccess) { nc = 0; (void)cudaGetLastError(); }
+        g_max_clusters[ri][CS] = nc;
+    }
+}
 static void fused_set_attributes()
 {
+    static bool done = false;
+    if (done) return;
+    done = true;
     SVD_CUDA_CHECK(cudaFuncSetAttribute(fused_pass_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FZ_SMEM_BYTES));
     SVD_CUDA_CHECK(cudaFuncSetAttribute(fused_pass_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FZ_SMEM_BYTES));
     SVD_CUDA_CHECK(cudaFuncSetAttribute(fused_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FZ_SMEM_BYTES));
+    query_clusters_t<2>(0);
+    query_clusters_t<4>(1);
+    query_clusters_t<8>(2);
+    if (getenv("SVD_GPU_VERBOSE")) {
+        fprintf(stderr, "fused pass: co-resident clusters by size 1..%d (RPT 8):", FZ_MAXCS);
+        for (int CS = 1; CS <= FZ_MAXCS; ++CS) fprintf(stderr, " %d", g_max_clusters[2][CS]);
+        fprintf(stderr, "\n");
+    }
+    const char *fc = getenv("SVD_GPU_FUSED_CS");       // experiments: smallest cluster size considered
+    if (fc) force_cs = atoi(fc);
 }
 
 void bidiag_device(int m, int n, double *A, long lda, double *alpha, double *beta, void *workspace,
@@ -820,7 +863,29 @@ void bidiag_device(int m, int n, double *A, long lda, double *alpha, double *bet
             fa.dots1 = dots1_ready ? b.dots1p : b.dots1; fa.nparts1 = dots1_ready ? dots1_parts : 0;
             fa.dots2p = b.dots2p; fa.alpha = alpha; fa.T = pl.T; fa.NC = pl.NC; fa.Lc = pl.Lc;
             fa.prefetch = (g_pdl && dots1_ready && k > 0) ? 1 : 0;   // predecessor is finish_xf (not the panel GEMM)
+            fa.trace = nullptr;
+            static unsigned long long *d_trace = nullptr;
+            const char *te = getenv("SVD_GPU_FZ_TRACE");
+            const bool tracing = te && atoi(te) == i;
+            if (tracing) {
+                if (!d_trace) SVD_CUDA_CHECK(cudaMalloc(&d_trace, 8 * 256 * sizeof(unsigned long long)));
+                SVD_CUDA_CHECK(cudaMemsetAsync(d_trace, 0, 8 * 256 * sizeof(unsigned long long), st));
+                fa.trace = d_trace;
+            }
             launch_fused(fa, pl, st);
+            if (tracing) {
+                static unsigned long long h[8 * 256];
+                SVD_CUDA_CHECK(cudaMemcpyAsync(h, d_trace, sizeof h, cudaMemcpyDeviceToHost, st));
+                SVD_CUDA_CHECK(cudaStreamSynchronize(st));
+                unsigned long long t0 = ~0ull;
+                for (int z = 0; z < 8 * 256; ++z) if (h[z] && h[z] < t0) t0 = h[z];
+                fprintf(stderr, "FZTRACE step %d CS %d Lc %d RPT %d T %d NC %d prefetch %d\n", i, pl.CS, pl.Lc, pl.RPT, pl.T, pl.NC, fa.prefetch);
+                for (int nt = 0; nt < 256 && h[nt * 8]; ++nt) {
+                    fprintf(stderr, "FZTRACE %3d", nt);
+                    for (int z = 0; z < 8; ++z) fprintf(stderr, " %8lld", h[nt * 8 + z] ? (long long)(h[nt * 8 + z] - t0) : -1ll);
+                    fprintf(stderr, "\n");
+                }
+            }
             if (Lb > 4096) {
                 const int nRowBlk = ceil_div(Lb, 128), nColBlk = ceil_div(R, 1024);
                 launch_finish_xf<4>(nRowBlk + nColBlk, st, A, lda, i, m, n, k, nb, b.P, b.ldp, b.Q, b.ldq, b.c,

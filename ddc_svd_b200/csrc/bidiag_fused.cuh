@@ -74,6 +74,7 @@ struct FusedArgs {
     double *dots2p;               // [cluster][2*NBMAX+2] partials of [Y^T r | U^T r | r.r] for finish_xf
     double *alpha;
     int T, NC, Lc;                // column tiles, clusters, rows per CTA (even)
+    unsigned long long *trace;    // debugging aid (SVD_GPU_FZ_TRACE=step): per-tile clock64 stamps of CTA 0, else null
     int prefetch;                 // 1: the preceding kernel does not write the trailing matrix, so the first
                                   //    tiles may be fetched before griddepcontrol.wait (programmatic dependent launch)
 };
@@ -163,6 +164,7 @@ __device__ __forceinline__ void fz_cluster_sync()
                  "barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
 
+#define FZ_TR(slot, nt) do { if (a.trace && blockIdx.x == 0 && (nt) < 256) a.trace[(nt) * 8 + (slot)] = clock64(); } while (0)
 // RPT = row pairs per sweep thread (rows per CTA <= 512*RPT <= 4096), CBW = 8/RPT columns per tile
 template <int RPT>
 __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedArgs a)
@@ -224,6 +226,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
                 int ncols = a.n - j0;
                 if (ncols > CBW) ncols = CBW;
                 const unsigned bytes = (unsigned)ncols * (unsigned)len * 8u;
+                FZ_TR(0, nt);
                 if (bytes) {
                     fz_mbar_arrive_expect_tx(full + nt, bytes);
                     for (int q = 0; q < ncols; ++q)
@@ -292,6 +295,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
                 int ncols = a.n - j0;
                 if (ncols > CBW) ncols = CBW;
                 const unsigned bytes = (unsigned)ncols * (unsigned)len * 8u;
+                FZ_TR(0, nt);
                 if (bytes) {
                     fz_mbar_arrive_expect_tx(full + s, bytes);
                     for (int q = 0; q < ncols; ++q)
@@ -354,6 +358,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
         for (int nt = 0; nt < ntiles; ++nt) {
             const int s = nt % FZ_STAGES, xs = nt % FZ_XR;
             fz_mbar_wait(wbar + s, (nt / FZ_STAGES) & 1);
+            if (lane == 0) FZ_TR(3, nt);
             double vals[CBW];
 #pragma unroll
             for (int qq = 0; qq < CBW; ++qq) {
@@ -388,6 +393,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
         for (int pt = 0; pt < ntiles; ++pt) {
             const int s = pt % FZ_STAGES, xs = pt % FZ_XR;
             fz_mbar_wait(xbar + xs, (pt / FZ_XR) & 1);
+            if (lane == 0) FZ_TR(4, pt);
             const int ncols = hn[s];
             const int j0 = i + 1 + (g + pt * NC) * CBW;
             double y = 0.0, r = 0.0;
@@ -400,6 +406,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
                 rq[s * FZ_CBW_MAX + lane] = r;
             }
             __syncwarp();
+            if (lane == 0) FZ_TR(5, pt);
             if (lane == 0) fz_mbar_arrive(rbar + s);
             if (crank == 0) {
                 if (lane < ncols) {
@@ -469,6 +476,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
         for (int nt = 0; nt < ntiles; ++nt) {
             const int s = nt % FZ_STAGES;
             fz_mbar_wait(full + s, (nt / FZ_STAGES) & 1);
+            if (wig == 0 && lane == 0) FZ_TR(1, nt);
             const int ncols = hn[s];
             const double *tl = tile + (size_t)s * FZ_STAGE;
 #pragma unroll
@@ -489,6 +497,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
                 if (lane == 0) wsum[(s * FZ_GW + wig) * FZ_CBW_MAX + q] = ps;
             }
             __syncwarp();
+            if (wig == 0 && lane == 0) FZ_TR(2, nt);
             if (lane == 0) fz_mbar_arrive(wbar + s);
         }
     } else {
@@ -502,6 +511,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
         for (int nt = 0; nt < ntiles; ++nt) {
             const int s = nt % FZ_STAGES;
             fz_mbar_wait(rbar + s, (nt / FZ_STAGES) & 1);
+            if (wig == 0 && lane == 0) FZ_TR(6, nt);
             const int ncols = hn[s];
             const double *tl = tile + (size_t)s * FZ_STAGE;
 #pragma unroll
@@ -520,6 +530,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
                 }
             }
             __syncwarp();
+            if (wig == 0 && lane == 0) FZ_TR(7, nt);
             if (lane == 0) fz_mbar_arrive(empty + s);
         }
 #pragma unroll

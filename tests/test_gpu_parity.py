@@ -119,7 +119,9 @@ def test_bidiag_fused_vs_split_many_tiles(D, shape):
     (Af, af, bf), (As, a_s, b_s) = out["1"], out["0"]
     for al, be in ((af, bf), (a_s, b_s)):
         assert abs(np.sum(al * al) + np.sum(be * be) - fro2) <= 1e-12 * fro2
-    assert np.abs(Af - As).max() <= 1e-9
+    # the two paths add the same terms in different orders; over thousands of steps the reflectors
+    # drift apart like n * eps * (growth), a few 1e-9 at n = 6144 — a race shows up as >= 1e-6
+    assert np.abs(Af - As).max() <= 1e-8
     assert np.abs(af - a_s).max() <= 1e-9 * np.abs(a_s).max() and np.abs(bf - b_s).max() <= 1e-9 * np.abs(a_s).max()
 
 
