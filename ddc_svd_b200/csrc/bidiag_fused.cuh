@@ -39,11 +39,12 @@ constexpr int FZ_XR = 16;                 // ring depth of the cross-CTA exchang
 constexpr int FZ_HW = 2;                  // helper warps (tile n is prepared by helper n % FZ_HW)
 constexpr int FZ_GW = 8;                  // warps per sweep group
 constexpr int FZ_GT = FZ_GW * 32;         // threads per sweep group
-// warp roles: 0 TMA producer | 1..HW helpers | HW+1 reducer | HW+2 finisher |
+// warp roles: 0 TMA producer | 1..HW helpers | HW+1 reducer | NFIN finishers |
 //             GW sweep-1 warps | GW sweep-2 warps
+constexpr int FZ_NFIN = 2;                // finisher warps (tile n is finished by finisher n % FZ_NFIN)
 constexpr int FZ_W_RED = 1 + FZ_HW;
 constexpr int FZ_W_FIN = 2 + FZ_HW;
-constexpr int FZ_W_S1 = 3 + FZ_HW;
+constexpr int FZ_W_S1 = FZ_W_FIN + FZ_NFIN;
 constexpr int FZ_W_S2 = FZ_W_S1 + FZ_GW;
 constexpr int FZ_WARPS = FZ_W_S2 + FZ_GW;
 constexpr int FZ_THREADS = FZ_WARPS * 32;
@@ -58,7 +59,8 @@ constexpr size_t FZ_SMEM_DOUBLES = (size_t)FZ_STAGES * FZ_STAGE                 
                                    + 5 * FZ_STAGES * FZ_CBW_MAX                      // corr, g, a_ij, y, r
                                    + FZ_STAGES * FZ_GW * FZ_CBW_MAX                  // per-warp column sums
                                    + FZ_XR * FZ_MAXCS * FZ_CBW_MAX                   // exchanged column sums
-                                   + 4 * NBMAX + 8;                                  // vTv, xTv, rowV, rowX, scalars
+                                   + 4 * NBMAX + 8                                   // vTv, xTv, rowV, rowX, scalars
+                                   + (FZ_NFIN - 1) * (2 * NBMAX + 2);                // panel-dot partials of the other finishers
 constexpr size_t FZ_SMEM_BYTES = FZ_SMEM_DOUBLES * 8 + (4 * FZ_STAGES + FZ_XR) * 8 + 16 * sizeof(int) + 128;
 
 struct FusedArgs {
@@ -185,7 +187,8 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
     double *s_rowV = s_xTv + NBMAX;
     double *s_rowX = s_rowV + NBMAX;
     double *s_sc = s_rowX + NBMAX;
-    uint64_t *full = reinterpret_cast<uint64_t *>(s_sc + 8);
+    double *s_fin = s_sc + 8;                                        // [FZ_NFIN-1][2*NBMAX+2]
+    uint64_t *full = reinterpret_cast<uint64_t *>(s_fin + (FZ_NFIN - 1) * (2 * NBMAX + 2));
     uint64_t *empty = full + FZ_STAGES;
     uint64_t *wbar = empty + FZ_STAGES;
     uint64_t *rbar = wbar + FZ_STAGES;
@@ -385,12 +388,15 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
                 }
             }
         }
-    } else if (warp == FZ_W_FIN) {
-        // ============================== finisher warp ==============================
+    } else if (warp < FZ_W_S1) {
+        // ============================== finisher warps ==============================
+        // (the per-tile latency chain of this role — barrier wake-up, smem reads, two stores, the
+        //  panel dots — is longer than the tile period, so tiles alternate between FZ_NFIN warps)
         // y_j, r_j of every tile column once the cluster-wide column sums are in; rank 0 also stores
         // them (new Y column, row vector r) and accumulates the panel dots Y^T r, U^T r, r.r
         double dY[2] = {0.0, 0.0}, dU[2] = {0.0, 0.0}, rr2 = 0.0, yr = 0.0;
-        for (int pt = 0; pt < ntiles; ++pt) {
+        const int fin = warp - FZ_W_FIN;
+        for (int pt = fin; pt < ntiles; pt += FZ_NFIN) {
             const int s = pt % FZ_STAGES, xs = pt % FZ_XR;
             fz_mbar_wait(xbar + xs, (pt / FZ_XR) & 1);
             if (lane == 0) FZ_TR(4, pt);
@@ -432,7 +438,28 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
             __syncwarp();
             if (lane == 0) fz_mbar_arrive(empty + s);
         }
-        if (crank == 0) {
+        // combine the finishers' partial panel dots in a fixed order: the others park theirs in
+        // shared memory, finisher 0 adds them up and writes the cluster's partial
+        if (fin > 0) {
+            double *sp = s_fin + (fin - 1) * S2;
+#pragma unroll
+            for (int z = 0; z < 2; ++z) {
+                const int kk = lane + 32 * z;
+                if (kk < k) { sp[kk] = dY[z]; sp[nb + kk] = dU[z]; }
+            }
+            if (lane == 0) { sp[k] = yr; sp[2 * nb] = rr2; }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(FZ_NFIN * 32) : "memory");
+        if (fin == 0 && crank == 0) {
+            for (int f2 = 1; f2 < FZ_NFIN; ++f2) {
+                const double *sp = s_fin + (f2 - 1) * S2;
+#pragma unroll
+                for (int z = 0; z < 2; ++z) {
+                    const int kk = lane + 32 * z;
+                    if (kk < k) { dY[z] += sp[kk]; dU[z] += sp[nb + kk]; }
+                }
+                if (lane == 0) { yr += sp[k]; rr2 += sp[2 * nb]; }
+            }
             double *out = a.dots2p + (long)g * S2;
 #pragma unroll
             for (int z = 0; z < 2; ++z) {
