@@ -31,6 +31,7 @@ constexpr int GT_CW = 4;          // columns per warp in gemvT
 constexpr int GT_WARPS = 8;
 constexpr int GN_THREADS = 256;   // each thread owns 2 rows in gemvN
 constexpr int GN_UNROLL = 8;
+constexpr int GN_CHUNK = 4096;    // columns of r staged in shared memory at a time (32 KB)
 
 // ---------------------------------------------------------------------------------------
 // block-wide dot of two strided-1 vectors (used by the "extra" CTAs)
@@ -137,35 +138,40 @@ gemvN_kernel(const double *__restrict__ A, long lda, int i, int m, int n, int mp
         if (threadIdx.x == 0) dots[slot] = d;
         return;
     }
-    extern __shared__ double s_rv[];
+    __shared__ double s_rv[GN_CHUNK];                         // r is staged GN_CHUNK columns at a time
     const int jbeg = i + 1 + blockIdx.y * colsPerSplit;
     const int jend = min(n, jbeg + colsPerSplit);
     if (jbeg >= jend) return;
-    for (int t = threadIdx.x; t < jend - jbeg; t += GN_THREADS) s_rv[t] = rv[jbeg + t];
-    __syncthreads();
     const int r = ((i + 1) & ~1) + (blockIdx.x * GN_THREADS + threadIdx.x) * 2;
-    if (r >= mpad) return;
-    const double *a = A + r + (long)jbeg * lda;
+    const bool live = r < mpad;
     double2 acc = make_double2(0.0, 0.0);
-    const int nc = jend - jbeg;
-    int j = 0;
-    for (; j + GN_UNROLL <= nc; j += GN_UNROLL) {
-        double2 av[GN_UNROLL];
+    for (int jc = jbeg; jc < jend; jc += GN_CHUNK) {
+        const int nc = min(GN_CHUNK, jend - jc);
+        if (jc > jbeg) __syncthreads();
+        for (int t = threadIdx.x; t < nc; t += GN_THREADS) s_rv[t] = rv[jc + t];
+        __syncthreads();
+        if (!live) continue;
+        const double *a = A + r + (long)jc * lda;
+        int j = 0;
+        for (; j + GN_UNROLL <= nc; j += GN_UNROLL) {
+            double2 av[GN_UNROLL];
 #pragma unroll
-        for (int u = 0; u < GN_UNROLL; ++u) av[u] = ldg_stream2(a + (long)(j + u) * lda);
+            for (int u = 0; u < GN_UNROLL; ++u) av[u] = ldg_stream2(a + (long)(j + u) * lda);
 #pragma unroll
-        for (int u = 0; u < GN_UNROLL; ++u) {
-            double w = s_rv[j + u];
-            acc.x += av[u].x * w;
-            acc.y += av[u].y * w;
+            for (int u = 0; u < GN_UNROLL; ++u) {
+                double w = s_rv[j + u];
+                acc.x += av[u].x * w;
+                acc.y += av[u].y * w;
+            }
+        }
+        for (; j < nc; ++j) {
+            double2 av = ldg_stream2(a + (long)j * lda);
+            double w = s_rv[j];
+            acc.x += av.x * w;
+            acc.y += av.y * w;
         }
     }
-    for (; j < nc; ++j) {
-        double2 av = ldg_stream2(a + (long)j * lda);
-        double w = s_rv[j];
-        acc.x += av.x * w;
-        acc.y += av.y * w;
-    }
+    if (!live) return;
     *reinterpret_cast<double2 *>(tmp + (long)blockIdx.y * ldt + r) = acc;
 }
 
@@ -665,20 +671,10 @@ static int launch_gemvN(const double *A, long lda, int i, int m, int n, int mpad
         if (nsplit < 1) nsplit = 1;
         if (nsplit > BIDIAG_MAX_SPLIT) nsplit = BIDIAG_MAX_SPLIT;
         colsPerSplit = (int)round_up(ceil_div(R, nsplit), 32);
-        if (colsPerSplit > 4096) colsPerSplit = 4096;           // smem staging of r
         nsplit = ceil_div(R, colsPerSplit);
-        if (nsplit > BIDIAG_MAX_SPLIT) {                        // extremely wide: bigger chunks
-            nsplit = BIDIAG_MAX_SPLIT;
-            colsPerSplit = (int)round_up(ceil_div(R, nsplit), 32);
-            nsplit = ceil_div(R, colsPerSplit);
-        }
     }
     dim3 grid(rowBlocks + 2 * k + 2, nsplit);
-    size_t smem = sizeof(double) * (size_t)colsPerSplit;
-    if (smem > 48 * 1024)
-        SVD_CUDA_CHECK(cudaFuncSetAttribute(gemvN_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)smem));
-    gemvN_kernel<<<grid, GN_THREADS, smem, st>>>(A, lda, i, m, n, mpad, b.rv, b.tmpN, lda, rowBlocks,
+    gemvN_kernel<<<grid, GN_THREADS, 0, st>>>(A, lda, i, m, n, mpad, b.rv, b.tmpN, lda, rowBlocks,
                                                  colsPerSplit, b.Q, b.ldq, nb, k, b.dots2);
     SVD_KERNEL_CHECK();
     return rowBlocks == 0 ? 0 : nsplit;

@@ -243,6 +243,20 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // every global load of the prologue that depends on nothing computed here is issued now, so the
+    // three dependent phases below do not each pay a trip to L2
+    double pro_pv = 0.0, pro_px = 0.0, pro_ci = 0.0;
+    if (tid < k) { pro_pv = a.P[i + (long)tid * a.ldp]; pro_px = a.P[i + (long)(nb + tid) * a.ldp]; }
+    if (tid == 32) pro_ci = a.c[i];
+    double2 creg[RPT];                                     // sweep-1 warps: their slice of the column c
+    if (warp >= FZ_W_S1 && warp < FZ_W_S2) {
+        const int gt0 = (warp - FZ_W_S1) * 32 + lane;
+#pragma unroll
+        for (int u = 0; u < RPT; ++u) {
+            const int lr = 2 * gt0 + 2 * FZ_GT * u;
+            creg[u] = (lr < len) ? *reinterpret_cast<const double2 *>(a.c + rs + lr) : make_double2(0.0, 0.0);
+        }
+    }
     // ---- combine the partial dots of the current column c (left by finish_xf) in a fixed order;
     //      the panel-row area is still unused and serves as scratch (the tiles may already be in flight)
     {
@@ -267,7 +281,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
         }
         __syncthreads();
         if (tid == 32) {
-            const double ci = a.c[i];
+            const double ci = pro_ci;
             Refl f = make_refl(ci, s_d1[2 * nb]);
             s_sc[0] = f.snu; s_sc[1] = f.inv; s_sc[2] = (ci + f.snu) * f.inv;
             if (g == 0 && crank == 0) a.alpha[i] = -f.snu;
@@ -275,7 +289,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
         __syncthreads();
         if (tid < k) {
             const double snu0 = s_sc[0], inv0 = s_sc[1];
-            const double pv = a.P[i + (long)tid * a.ldp], px = a.P[i + (long)(nb + tid) * a.ldp];
+            const double pv = pro_pv, px = pro_px;
             s_rowV[tid] = pv;
             s_rowX[tid] = px;
             s_vTv[tid] = (s_d1[tid] + snu0 * pv) * inv0;
@@ -474,12 +488,6 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
         // No barrier between the warps: each one runs ahead to the next tile as soon as it has landed.
         const int wig = warp - FZ_W_S1;
         const int gt = wig * 32 + lane;
-        double2 creg[RPT];
-#pragma unroll
-        for (int u = 0; u < RPT; ++u) {
-            const int lr = 2 * gt + 2 * FZ_GT * u;
-            creg[u] = (lr < len) ? *reinterpret_cast<const double2 *>(a.c + rs + lr) : make_double2(0.0, 0.0);
-        }
         if (g == 0) {
             // the reflector itself: v = (c + s*nu*e_i) * inv, in place and into the V panel
 #pragma unroll

@@ -20,6 +20,8 @@ typedef struct {
     void *stream, *copy_stream;
     void *ev[6];
     void *ev_copy;
+    void *ev_first;           /* the first of U / V to be final (the other one is still being back-transformed) */
+    int first_is_u, first_recorded;
     void *arena;
     size_t arena_bytes;
     int nb, rqi;
@@ -55,6 +57,7 @@ static void ctx_init(void)
     g.copy_stream = svdgpu_stream_create();
     for (int i = 0; i < 6; ++i) g.ev[i] = svdgpu_event_create();
     g.ev_copy = svdgpu_event_create();
+    g.ev_first = svdgpu_event_create();
     g.inited = 1;
 }
 
@@ -125,6 +128,7 @@ static void vectors_core(int m, int n, const double *dA, long lda, const double 
                            g.rqi, work, stream);
     if (ev_mid) svdgpu_event_record(ev_mid, stream);
     svdgpu_wy_apply(1, m, n_left(m, n), dA, lda, dU, ldu, ns, work, stream);
+    svdgpu_event_record(g.ev_first, stream); g.first_is_u = 1; g.first_recorded = 1;
     svdgpu_wy_apply(0, n, n_right(m, n), dA, lda, dV, ldv, ns, work, stream);
 }
 
@@ -188,6 +192,7 @@ static void svd_dev_inner(int m, int n, double *dA, long lda, double *dsigma, do
             svdgpu_event_record(g.ev[3], stream);
             svdgpu_wy_apply(1, n, n_left(n, n), dR, ldr, dU, ldu, n, work, stream);
             svdgpu_wy_apply(0, n, n_right(n, n), dR, ldr, dV, ldv, n, work, stream);
+            svdgpu_event_record(g.ev_first, stream); g.first_is_u = 0; g.first_recorded = 1;
             svdgpu_wy_apply(1, m, n, dA, lda, dU, ldu, n, work, stream);      /* U = Q [U_R; 0] */
         } else {
             svdgpu_event_record(g.ev[3], stream);
@@ -276,6 +281,7 @@ void svd_gpu(int m, int n, double *A, double *sigma, double *U, double *V)
     svdgpu_stream_sync(g.stream);
     g.ms[0] = (float)(wall_ms() - t_h2d0);
 
+    g.first_recorded = 0;
     svd_dev_inner(m, n, dA, lda, dsig_final, dU, m, dV, n, scratch, g.stream, g.ev_copy);
 
     /* device -> host.  The reflector matrix goes back on the copy stream as soon as the
@@ -283,13 +289,21 @@ void svd_gpu(int m, int n, double *A, double *sigma, double *U, double *V)
     svdgpu_stream_wait_event(g.copy_stream, g.ev_copy);
     if (lda == m) svdgpu_d2h(A, dA, sizeof(double) * (size_t)m * n, g.copy_stream);
     else svdgpu_d2h_2d(A, sizeof(double) * m, dA, sizeof(double) * lda, sizeof(double) * m, n, g.copy_stream);
+    /* ... and so does whichever of U / V is final first, while the other is still being back-transformed.
+     * Only the first min(m,n) columns are written (svd_gpu.c:118-121). */
+    int early = -1;                                   /* 1: U went on the copy stream, 0: V */
+    if (want_vec && g.first_recorded) {
+        early = g.first_is_u;
+        svdgpu_stream_wait_event(g.copy_stream, g.ev_first);
+        if (early) svdgpu_d2h(U, dU, sizeof(double) * (size_t)m * mn, g.copy_stream);
+        else svdgpu_d2h(V, dV, sizeof(double) * (size_t)n * mn, g.copy_stream);
+    }
     svdgpu_stream_sync(g.stream);
     const double t_d2h0 = wall_ms();
     svdgpu_d2h(sigma, dsig_final, sizeof(double) * (size_t)mn, g.stream);
     if (want_vec) {
-        /* only the first min(m,n) columns are written (svd_gpu.c:118-121) */
-        svdgpu_d2h(U, dU, sizeof(double) * (size_t)m * mn, g.stream);
-        svdgpu_d2h(V, dV, sizeof(double) * (size_t)n * mn, g.stream);
+        if (early != 1) svdgpu_d2h(U, dU, sizeof(double) * (size_t)m * mn, g.stream);
+        if (early != 0) svdgpu_d2h(V, dV, sizeof(double) * (size_t)n * mn, g.stream);
     }
     svdgpu_stream_sync(g.stream);
     svdgpu_stream_sync(g.copy_stream);

@@ -306,7 +306,7 @@ def test_multU_multV_reference_signatures(D):
 
 # ------------------------------------------------------------------ the whole path
 @pytest.mark.parametrize("shape", [(1, 1), (2, 2), (3, 3), (5, 5), (64, 64), (100, 100), (256, 256), (512, 512),
-                                   (1024, 1024), (700, 500), (500, 700), (1025, 33), (33, 1025)])
+                                   (1024, 1024), (700, 500), (500, 700), (1025, 33), (33, 1025), (300, 40000)])
 def test_svd_gpu_vs_lapack(D, shape):
     m, n = shape
     A = util.rand_matrix(m, n)                                 # test-whole-svd.c recipe
@@ -341,6 +341,38 @@ def test_svd_gpu_vs_oracle_512(D):
     # we are strictly more accurate than the reference on its own input
     sv = np.linalg.svd(A, compute_uv=False)[::-1]
     assert np.abs(sigma - sv).max() < 1e-3 * np.abs(s_o - sv).max()
+
+
+# ------------------------------------------------------------------ the FP64 DMMA GEMM building block
+@pytest.mark.parametrize("case", [(0, 0, 130, 70, 50), (1, 0, 64, 200, 333), (0, 1, 257, 129, 64), (1, 1, 65, 66, 67),
+                                  (0, 1, 1000, 900, 64), (0, 0, 700, 513, 128), (0, 1, 256, 256, 16),
+                                  (0, 0, 1531, 777, 100), (0, 1, 4100, 300, 64)])
+@pytest.mark.parametrize("alpha_beta", [(-1.0, 1.0), (1.0, 1.0), (0.5, 0.0)])
+def test_dgemm_vs_numpy(D, case, alpha_beta):
+    # (transA, transB, M, N, K); alpha = +-1 with beta = 1 and M, N >= 256 takes the persistent
+    # rank-K update kernel, everything else the generic one
+    ta, tb, M, N, K = case
+    alpha, beta = alpha_beta
+    L = D.lib()
+    rng = np.random.default_rng(M + N + K)
+    A = rng.standard_normal((M, K)); B = rng.standard_normal((K, N)); C = rng.standard_normal((M, N))
+    As = np.asfortranarray(A.T if ta else A); Bs = np.asfortranarray(B.T if tb else B); Cs = np.asfortranarray(C)
+    bufs = []
+    def put(a):
+        d = L.svdgpu_malloc(a.nbytes); bufs.append(d)
+        L.svdgpu_h2d(d, util.p(a), a.nbytes, None)
+        return d
+    try:
+        dA, dB, dC = put(As), put(Bs), put(Cs)
+        L.svdgpu_dgemm(ta, tb, M, N, K, alpha, dA, As.shape[0], dB, Bs.shape[0], beta, dC, M, None)
+        out = np.empty((M, N), order="F")
+        L.svdgpu_d2h(util.p(out), dC, out.nbytes, None)
+        L.svdgpu_stream_sync(None)
+    finally:
+        for d in bufs:
+            L.svdgpu_free(d)
+    ref = beta * C + alpha * (A @ B)
+    assert np.abs(out - ref).max() <= 50 * EPS * K * max(1.0, np.abs(ref).max())
 
 
 # ------------------------------------------------------------------ QR first (m >> n)
