@@ -304,20 +304,26 @@ def run_own(args):
         wbytes = L.svdgpu_bidiag_workspace(m, n, m)
         work = torch.zeros(wbytes // 8 + 8, dtype=torch.float64, device=dev)
         probe = {}
-        for wh, nm in ((0, "gemvT"), (1, "gemvN")):
+        scratchA = A_master.clone()            # the fused probe writes a reflector into column 0
+        for wh, nm in ((0, "gemvT"), (1, "gemvN"), (2, "fused")):
+            src = scratchA if wh == 2 else A_master
             for _ in range(3):
-                L.svdgpu_bidiag_pass_probe(m, n, A_master.data_ptr(), m, work.data_ptr(), wh, stream)
+                L.svdgpu_bidiag_pass_probe(m, n, src.data_ptr(), m, work.data_ptr(), wh, stream)
             p0 = torch.cuda.Event(enable_timing=True); p1 = torch.cuda.Event(enable_timing=True)
             reps = 10
             tot = 0.0
             for _ in range(reps):
                 flush.zero_()
                 p0.record()
-                L.svdgpu_bidiag_pass_probe(m, n, A_master.data_ptr(), m, work.data_ptr(), wh, stream)
+                L.svdgpu_bidiag_pass_probe(m, n, src.data_ptr(), m, work.data_ptr(), wh, stream)
                 p1.record()
                 torch.cuda.synchronize()
                 tot += p0.elapsed_time(p1)
-            probe[nm + "_full_pass_gbs"] = 8.0 * m * n / (tot / reps * 1e-3) / 1e9
+            probe[nm + "_full_pass_gbs"] = 8.0 * m * (n - 1 if wh == 2 else n) / (tot / reps * 1e-3) / 1e9
+            if wh == 2:
+                probe["fused_full_pass_us"] = tot / reps * 1e3
+                probe["fused_full_pass_frac_of_peak"] = probe[nm + "_full_pass_gbs"] / pk["hbm_gbs"]
+        del scratchA
         t_bd = ph[1] * 1e-3
         ach_survey = b_survey / t_bd / 1e9          # SURVEY.md 8(d) definition: B_alg = 8 * 1.5 * S
         ach_own = b_alg / t_bd / 1e9                # bytes our scheme actually has to move

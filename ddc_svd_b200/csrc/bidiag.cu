@@ -941,7 +941,24 @@ void bidiag_pass_probe(int m, int n, const double *A, long lda, void *workspace,
     int targetT, targetN;
     sm_targets(targetT, targetN);
     if (which == 0) launch_gemvT(A, lda, 0, m, n, mpad, b, 32, 0, targetT, st);
-    else            launch_gemvN(A, lda, 0, m, n, mpad, b, 32, 0, targetN, st);
+    else if (which == 1) launch_gemvN(A, lda, 0, m, n, mpad, b, 32, 0, targetN, st);
+    else {
+        // the fused single-read pass of step 0 (writes the reflector into column 0 of A and panel
+        // scratch in the workspace: hand it a scratch copy of the matrix)
+        int dev = 0, nsm = 148;
+        SVD_CUDA_CHECK(cudaGetDevice(&dev));
+        SVD_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+        fused_set_attributes();
+        const FusedPlan pl = plan_fused(0, m, n, mpad, nsm, 2, 1);
+        if (!pl.ok) return;
+        FusedArgs fa;
+        fa.A = const_cast<double *>(A); fa.lda = lda; fa.i = 0; fa.m = m; fa.n = n; fa.mpad = mpad; fa.k = 0; fa.nb = 32;
+        fa.P = b.P; fa.ldp = b.ldp; fa.Q = b.Q; fa.ldq = b.ldq; fa.c = b.c; fa.rv = b.rv;
+        fa.tmpN = b.tmpN; fa.ldt = lda; fa.dots1 = b.dots1; fa.nparts1 = 0; fa.dots2p = b.dots2p;
+        fa.alpha = b.dots2;                      // scratch: the probe has no alpha array
+        fa.T = pl.T; fa.NC = pl.NC; fa.Lc = pl.Lc; fa.trace = nullptr; fa.prefetch = 0;
+        launch_fused(fa, pl, st);
+    }
 }
 
 } // namespace svdgpu

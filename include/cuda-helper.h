@@ -84,8 +84,9 @@ void   svdgpu_dgemm(int transA, int transB, int M, int N, int K, double alpha, c
  * multiplies dx[0..n) by *dfactor (used to scale sigma back). */
 void   svdgpu_scale_matrix(int m, int n, double *dA, long lda, double *dscale, double *dwork, void *stream);
 void   svdgpu_scale_vector(int n, double *dx, const double *dfactor, void *stream);
-/* one gemvT + one gemvN pass over the full m x n matrix (the two streaming kernels of the
- * bidiagonalization), for roofline measurement; returns nothing, only enqueues. */
+/* one streaming pass over the full m x n matrix, for roofline measurement: which = 0 gemvT, 1 gemvN
+ * (the split passes), 2 the fused single-read pass of step 0 (writes a reflector into column 0 of dA:
+ * hand it a scratch copy); returns nothing, only enqueues. */
 void   svdgpu_bidiag_pass_probe(int m, int n, const double *dA, long lda, void *dwork, int which,
                                 void *stream);
 
