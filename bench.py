@@ -31,12 +31,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE captured launch of the dominant kernel
-# (ncu --set full, profiles/r01_ncu_summary_v2.md): fused_pass_kernel at step i=1500 of n=16384
+# (ncu --set full, profiles/r01_ncu_summary_v3.md): fused_pass_kernel at step i=1500 of n=16384
 # (algorithmic single-read bytes of that launch: 8*(16384-1500)*(16384-1501) = 1.772e9)
-NCU_TRAFFIC = {16384: 1.784272e9 + 9.264e6, 4096: 77.358e6 + 2.543e6}
+NCU_TRAFFIC = {16384: 1.780507e9 + 5.105664e6, 4096: 77.380864e6 + 1.881856e6}
 NCU_TRAFFIC_NOTE = ("dram__bytes_read.sum + dram__bytes_write.sum of ONE fused_pass_kernel launch (ncu --set full): "
                     "n=16384 step 1500 (single-read algorithmic bytes of that launch 1.772e9), "
-                    "n=4096 step 1000 (76.7e6); profiles/r01_ncu_summary_v2.md")
+                    "n=4096 step 1000 (76.7e6); profiles/r01_ncu_summary_v3.md")
 METRIC = "svd_gpu seconds"
 UNIT = "s"
 

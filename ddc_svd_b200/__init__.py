@@ -96,6 +96,7 @@ SIGNATURES = [
     ("svdgpu_twisted_vectors", None, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                       c_long, c_void_p, c_long, c_void_p, c_int, c_void_p, c_void_p]),
     ("svdgpu_backtransform_workspace", c_size_t, [c_int, c_int, c_int]),
+    ("svdgpu_transpose", None, [c_int, c_int, c_void_p, c_long, c_void_p, c_long, c_void_p]),
     ("svdgpu_qr_workspace", c_size_t, [c_int, c_int]),
     ("svdgpu_qr", None, [c_int, c_int, c_void_p, c_long, c_void_p, c_long, c_void_p, c_void_p]),
     ("svdgpu_wy_apply", None, [c_int, c_int, c_int, c_void_p, c_long, c_void_p, c_long, c_int, c_void_p, c_void_p]),

@@ -71,6 +71,7 @@ struct GemmArgs {
     int splitk; long sSplit;
 };
 void dgemm_dmma(const GemmArgs &g, cudaStream_t st);
+void transpose_device(int m, int n, const double *A, long lda, double *At, long ldat, cudaStream_t st);
 // out(MxN, ldo) = beta*out + alpha * sum_s part[s]  (deterministic split-K reduction)
 void sum_partials(double *out, long ldo, const double *part, long ldp, long sSplit, int nsplit,
                   int M, int N, double alpha, double beta, cudaStream_t st);

@@ -167,6 +167,10 @@ void svdgpu_scale_matrix(int m, int n, double *dA, long lda, double *dscale, dou
 {
     scale_matrix_device(m, n, dA, lda, dscale, dwork, S(stream));
 }
+void svdgpu_transpose(int m, int n, const double *dA, long lda, double *dAt, long ldat, void *stream)
+{
+    transpose_device(m, n, dA, lda, dAt, ldat, S(stream));
+}
 void svdgpu_scale_vector(int n, double *dx, const double *dfactor, void *stream)
 {
     scale_vector_device(n, dx, dfactor, S(stream));

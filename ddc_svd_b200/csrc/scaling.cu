@@ -78,4 +78,28 @@ void scale_vector_device(int n, double *x, const double *factor, cudaStream_t st
     SVD_KERNEL_CHECK();
 }
 
+// At (n x m, ldat) = A^T (A is m x n, lda): 32 x 32 tiles through padded shared memory
+__global__ void transpose_kernel(const double *__restrict__ A, long lda, int m, int n, double *__restrict__ At, long ldat)
+{
+    __shared__ double tile[32][33];
+    const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int r = r0 + threadIdx.x, c = c0 + j;
+        if (r < m && c < n) tile[j][threadIdx.x] = A[r + (long)c * lda];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int c = c0 + threadIdx.x, r = r0 + j;
+        if (r < m && c < n) At[c + (long)r * ldat] = tile[threadIdx.x][j];
+    }
+}
+void transpose_device(int m, int n, const double *A, long lda, double *At, long ldat, cudaStream_t st)
+{
+    if (m <= 0 || n <= 0) return;
+    const dim3 grid(ceil_div(m, 32), ceil_div(n, 32));
+    if (grid.y > 65535) { fprintf(stderr, "transpose_device: n too large (%d)\n", n); abort(); }
+    transpose_kernel<<<grid, dim3(32, 8), 0, st>>>(A, lda, m, n, At, ldat);
+    SVD_KERNEL_CHECK();
+}
+
 } // namespace svdgpu

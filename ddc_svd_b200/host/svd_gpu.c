@@ -27,6 +27,7 @@ typedef struct {
     int nb, rqi;
     int qr_first;             /* 1: m >= qr_ratio10/10 * n goes through QR first */
     int qr_ratio10;
+    int wide_transpose;       /* 1: m < n is solved as the SVD of A^T (U and V swapped) */
     float ms[7];
     int ms_pending;           /* events recorded but not yet read */
 } svd_ctx;
@@ -48,9 +49,10 @@ static void ctx_init(void)
     const char *e;
     (void)svdgpu_device_count();                 /* aborts loudly when there is no GPU */
     if ((e = getenv("SVD_GPU_DEVICE")) != NULL) svdgpu_set_device(atoi(e));
-    g.nb = 32; g.rqi = 1; g.qr_first = 1; g.qr_ratio10 = 25;
+    g.nb = 32; g.rqi = 1; g.qr_first = 1; g.qr_ratio10 = 25; g.wide_transpose = 1;
     if ((e = getenv("SVD_GPU_QR_FIRST")) != NULL) g.qr_first = atoi(e);
     if ((e = getenv("SVD_GPU_QR_RATIO10")) != NULL) g.qr_ratio10 = atoi(e);
+    if ((e = getenv("SVD_GPU_WIDE_TRANSPOSE")) != NULL) g.wide_transpose = atoi(e);
     if ((e = getenv("SVD_GPU_NB")) != NULL) g.nb = atoi(e);
     if ((e = getenv("SVD_GPU_RQI")) != NULL) g.rqi = atoi(e);
     g.stream = svdgpu_stream_create();
@@ -68,6 +70,7 @@ void svd_gpu_set_option(const char *name, int value)
     else if (!strcmp(name, "rqi")) g.rqi = value;
     else if (!strcmp(name, "qr_first")) g.qr_first = value;
     else if (!strcmp(name, "qr_ratio10")) g.qr_ratio10 = value;
+    else if (!strcmp(name, "wide_transpose")) g.wide_transpose = value;
     else if (!strcmp(name, "release")) {          /* drop the cached device arena */
         svdgpu_free(g.arena); g.arena = NULL; g.arena_bytes = 0;
     } else { fprintf(stderr, "svd_gpu_set_option: unknown option '%s'\n", name); abort(); }
@@ -154,22 +157,18 @@ void svd_gpu_vectors_dev(int m, int n, const double *dA_mod, long lda, const dou
                  stream, NULL);
 }
 
-static void svd_dev_inner(int m, int n, double *dA, long lda, double *dsigma, double *dU, long ldu, double *dV,
-                          long ldv, char *scratch, void *stream, void *ev_after_bidiag_for_copy)
+static void svd_dev_direct(int m, int n, double *dA, long lda, double *dsigma, double *dU, long ldu, double *dV,
+                           long ldv, char *scratch, void *stream, void *ev_after_bidiag_for_copy, int record_start)
 {
     const int mn = m < n ? m : n;
     const int want_vec = (dU != NULL && dV != NULL);
-    if ((dU == NULL) != (dV == NULL)) {
-        fprintf(stderr, "svd_gpu: U and V must both be given or both be NULL (values only)\n");
-        abort();
-    }
     double *dalpha = (double *)scratch;             scratch += up256(sizeof(double) * (size_t)mn);
     double *dbeta = (double *)scratch;              scratch += up256(sizeof(double) * ((size_t)mn + 1));
     double *dsig = (double *)scratch;               scratch += up256(sizeof(double) * (size_t)mn);
     double *dscale = (double *)scratch;             scratch += 256;
     void *work = scratch;
 
-    svdgpu_event_record(g.ev[0], stream);
+    if (record_start) svdgpu_event_record(g.ev[0], stream);
     /* range guard: exact power-of-two scaling when max|A| is far from 1 (sigma is scaled back below) */
     svdgpu_scale_matrix(m, n, dA, lda, dscale, (double *)work, stream);
     svdgpu_memset(dbeta, 0, sizeof(double) * ((size_t)mn + 1), stream);
@@ -221,6 +220,43 @@ static size_t small_bytes(int mn)
 {
     return 2 * up256(sizeof(double) * (size_t)mn) + up256(sizeof(double) * ((size_t)mn + 1)) + 256;
 }
+static size_t direct_scratch_bytes(int m, int n, int ns, long lda)
+{
+    return small_bytes(m < n ? m : n) + maxz(phase_work_bytes(m, n, ns, lda), qr_extra_bytes(m, n, ns));
+}
+/* wide inputs: A^T = V S U^T is a tall problem, which gets the left vectors from their own twisted
+ * factorization (and the QR-first route when n >> m) */
+static int use_wide_transpose(int m, int n) { return g.wide_transpose && m < n; }
+static size_t scratch_bytes(int m, int n, int ns, long lda)
+{
+    if (!use_wide_transpose(m, n)) return direct_scratch_bytes(m, n, ns, lda);
+    const long ldt = (n + 1) / 2 * 2;
+    return up256(sizeof(double) * (size_t)ldt * m) + direct_scratch_bytes(n, m, ns, ldt);
+}
+
+static void svd_dev_inner(int m, int n, double *dA, long lda, double *dsigma, double *dU, long ldu, double *dV,
+                          long ldv, char *scratch, void *stream, void *ev_after_bidiag_for_copy)
+{
+    if ((dU == NULL) != (dV == NULL)) {
+        fprintf(stderr, "svd_gpu: U and V must both be given or both be NULL (values only)\n");
+        abort();
+    }
+    if (!use_wide_transpose(m, n)) {
+        svd_dev_direct(m, n, dA, lda, dsigma, dU, ldu, dV, ldv, scratch, stream, ev_after_bidiag_for_copy, 1);
+        return;
+    }
+    const long ldt = (n + 1) / 2 * 2;
+    double *dAt = (double *)scratch;
+    scratch += up256(sizeof(double) * (size_t)ldt * m);
+    svdgpu_event_record(g.ev[0], stream);
+    if (ldt != n) svdgpu_memset(dAt, 0, sizeof(double) * (size_t)ldt * m, stream);
+    svdgpu_transpose(m, n, dA, lda, dAt, ldt, stream);
+    svd_dev_direct(n, m, dAt, ldt, dsigma, dV, ldv, dU, ldu, scratch, stream, NULL, 0);
+    g.first_is_u = !g.first_is_u;
+    /* A leaves as the transpose of the tall problem's reflector storage */
+    svdgpu_transpose(n, m, dAt, ldt, dA, lda, stream);
+    if (ev_after_bidiag_for_copy) svdgpu_event_record(ev_after_bidiag_for_copy, stream);
+}
 
 void svd_gpu_dev(int m, int n, double *dA, long lda, double *dsigma, double *dU, long ldu, double *dV, long ldv,
                  void *stream)
@@ -228,7 +264,7 @@ void svd_gpu_dev(int m, int n, double *dA, long lda, double *dsigma, double *dU,
     ctx_init();
     const int mn = m < n ? m : n;
     const int ns = (dU && dV) ? mn : 0;
-    char *scratch = arena_get(small_bytes(mn) + maxz(phase_work_bytes(m, n, ns, lda), qr_extra_bytes(m, n, ns)));
+    char *scratch = arena_get(scratch_bytes(m, n, ns, lda));
     g.ms[0] = g.ms[5] = 0.f;
     svd_dev_inner(m, n, dA, lda, dsigma, dU, ldu, dV, ldv, scratch, stream, NULL);
 }
@@ -261,9 +297,8 @@ void svd_gpu(int m, int n, double *A, double *sigma, double *U, double *V)
     const size_t bytesA = up256(sizeof(double) * (size_t)lda * n);
     const size_t bytesU = want_vec ? up256(sizeof(double) * (size_t)m * mn) : 0;
     const size_t bytesV = want_vec ? up256(sizeof(double) * (size_t)n * mn) : 0;
-    char *base = arena_get(bytesA + bytesU + bytesV + up256(sizeof(double) * (size_t)mn) + small_bytes(mn) +
-                           maxz(phase_work_bytes(m, n, want_vec ? mn : 0, lda),
-                                qr_extra_bytes(m, n, want_vec ? mn : 0)));
+    char *base = arena_get(bytesA + bytesU + bytesV + up256(sizeof(double) * (size_t)mn) +
+                           scratch_bytes(m, n, want_vec ? mn : 0, lda));
     double *dA = (double *)base;
     double *dU = want_vec ? (double *)(base + bytesA) : NULL;
     double *dV = want_vec ? (double *)(base + bytesA + bytesU) : NULL;

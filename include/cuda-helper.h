@@ -84,6 +84,9 @@ void   svdgpu_dgemm(int transA, int transB, int M, int N, int K, double alpha, c
  * multiplies dx[0..n) by *dfactor (used to scale sigma back). */
 void   svdgpu_scale_matrix(int m, int n, double *dA, long lda, double *dscale, double *dwork, void *stream);
 void   svdgpu_scale_vector(int n, double *dx, const double *dfactor, void *stream);
+/* dAt (n x m, ldat) = dA^T (m x n, lda), on the device: replaces the host transpose of
+ * matrix_helper.c:166-174 (svd_gpu.c:104) and turns a wide problem into a tall one */
+void   svdgpu_transpose(int m, int n, const double *dA, long lda, double *dAt, long ldat, void *stream);
 /* one streaming pass over the full m x n matrix, for roofline measurement: which = 0 gemvT, 1 gemvN
  * (the split passes), 2 the fused single-read pass of step 0 (writes a reflector into column 0 of dA:
  * hand it a scratch copy); returns nothing, only enqueues. */

@@ -465,6 +465,51 @@ def test_svd_gpu_graded_spectrum_keeps_U_orthogonal(D):
     assert np.linalg.norm(A - (U * sigma) @ V.T) / np.linalg.norm(A) <= c
 
 
+@pytest.mark.parametrize("shape", [(200, 300), (300, 200), (120, 900), (900, 120)])
+def test_svd_gpu_graded_spectrum_rectangular(D, shape):
+    # same, for tall and wide inputs: a wide matrix is solved as the SVD of its transpose, so its U
+    # (the transposed problem's V) is as orthogonal as any other; the old wide route (option
+    # "wide_transpose" = 0) takes y = B x / sigma and is only held to the residual bound
+    m, n = shape
+    mn = min(m, n)
+    rng = np.random.default_rng(1)
+    Q1, _ = np.linalg.qr(rng.standard_normal((m, mn))); Q2, _ = np.linalg.qr(rng.standard_normal((n, mn)))
+    sv = np.logspace(0, -10, mn)
+    A = (Q1 * sv) @ Q2.T
+    sigma, U, V, _ = D.svd_gpu(A)
+    c = 100 * EPS * max(m, n)
+    assert np.abs(sigma - sv[::-1]).max() <= 10 * EPS * max(m, n)
+    assert np.linalg.norm(U.T @ U - np.eye(mn)) <= c and np.linalg.norm(V.T @ V - np.eye(mn)) <= c
+    assert np.linalg.norm(A - (U * sigma) @ V.T) / np.linalg.norm(A) <= c
+    if m < n:
+        D.set_option("wide_transpose", 0)
+        try:
+            s0, U0, V0, A0 = D.svd_gpu(A)
+        finally:
+            D.set_option("wide_transpose", 1)
+        assert np.abs(s0 - sigma).max() <= 10 * EPS * max(m, n)
+        assert np.linalg.norm(A - (U0 * s0) @ V0.T) / np.linalg.norm(A) <= c
+
+
+def test_svd_gpu_wide_direct_route_keeps_reference_reflectors(D):
+    # option "wide_transpose" = 0: a wide input is bidiagonalized as it is and A leaves as the
+    # reference's reflector storage (bidiag.c:33-186); the default route returns the transposed
+    # problem's storage instead
+    A = util.rand_matrix(90, 130)
+    D.set_option("wide_transpose", 0)
+    try:
+        s0, U0, V0, A0 = D.svd_gpu(A)
+    finally:
+        D.set_option("wide_transpose", 1)
+    Ao, _, _ = util.oracle_bidiag(A)
+    assert np.abs(A0 - Ao).max() <= 1e-9
+    check_lapack_bounds(A, s0, U0, V0)
+    s1, U1, V1, A1 = D.svd_gpu(A)
+    check_lapack_bounds(A, s1, U1, V1)
+    At, _, _ = util.oracle_bidiag(np.ascontiguousarray(A.T))
+    assert np.abs(A1 - At.T).max() <= 1e-9
+
+
 # ------------------------------------------------------------------ benchmark sizes: properties
 def test_svd_gpu_4096_properties(D):
     # BASELINE.json configs[1]; LAPACK for sigma, size-independent properties for the vectors
