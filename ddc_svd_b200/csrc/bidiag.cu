@@ -438,12 +438,14 @@ finish_xf_kernel(double *__restrict__ A, long lda, int i, int m, int n, int k, i
                  double *__restrict__ dots1p)
 {
     constexpr int S = DOT_SLOTS_C;
-    __shared__ double s_part[7][S];
     __shared__ double s_d[S];
     __shared__ double s_yTu[NBMAX], s_uTu[NBMAX], s_rowY[NBMAX], s_rowU[NBMAX];
     __shared__ double s_red[3][XF_SL][33];
     __shared__ double s_red2[3][8][32];
     __shared__ double s_c[32], s_x[32];
+    // the prologue's partial sums live in s_red's storage (used only after they are consumed)
+    static_assert(15 * DOT_SLOTS_C <= 3 * XF_SL * 33, "s_part does not fit into s_red");
+    double(*s_part)[S] = reinterpret_cast<double(*)[S]>(&s_red[0][0][0]);
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     const int R = n - i - 1, Lb = m - i - 1;
     const bool rowblk = (int)blockIdx.x < nRowBlk;
@@ -461,29 +463,48 @@ finish_xf_kernel(double *__restrict__ A, long lda, int i, int m, int n, int k, i
 #pragma unroll
     for (int z = 0; z < ZX; ++z) { const int q = w + XF_SL * z; xk[z] = (live && q < k) ? P[(i + 1 + idx) + (long)(nb + q) * ldp] : 0.0; }
     if (live) {
-        for (int sp = w; sp < nsplit; sp += XF_SL) tt += tmp[(long)sp * ldt + i + 1 + idx];
+        // all of this slice's partials in flight at once (<= 5 for up to 160 clusters)
+        for (int sp0 = w; sp0 < nsplit; sp0 += 5 * XF_SL) {
+            double tv[5];
+#pragma unroll
+            for (int u = 0; u < 5; ++u) {
+                const int sp = sp0 + u * XF_SL;
+                tv[u] = (sp < nsplit) ? tmp[(long)sp * ldt + i + 1 + idx] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 5; ++u) tt += tv[u];
+        }
         if (w == 0) ar = A[(i + 1 + idx) + (long)(i + 1) * lda];
     }
     const double rf = rv[i + 1];
     double qy = 0.0, qu = 0.0;
     if (t <= k) qy = Q[(i + 1) + (long)t * ldq];
     if (t < k) qu = Q[(i + 1) + (long)(nb + t) * ldq];
-    // ---- combine the pass's partial dots: entries [0..k], [nb..nb+k), [2nb]; 7 threads per entry
+    // ---- combine the pass's partial dots: entries [0..k], [nb..nb+k), [2nb]; TPE threads per entry,
+    //      each with all the loads of its chunk in flight at once
+    const int ne = 2 * k + 2;
+    const int TPE = (ne <= 68) ? 15 : 7;                    // 1024 threads: 68 x 15 or 130 x 7
     {
-        const int ne = 2 * k + 2, e = t / 7, part = t - 7 * e;
+        const int e = t / TPE, part = t - TPE * e;
         if (e < ne) {
             const int slot = (e <= k) ? e : (e <= 2 * k ? nb + (e - k - 1) : 2 * nb);
-            const int chunk = (nparts2 + 6) / 7, p0 = part * chunk, p1 = min(nparts2, p0 + chunk);
+            const int chunk = (nparts2 + TPE - 1) / TPE, p0 = part * chunk, p1 = min(nparts2, p0 + chunk);
+            constexpr int LB = 10;
             double a2 = 0.0;
-            for (int pz = p0; pz < p1; ++pz) a2 += dots2p[(long)pz * S + slot];
+            for (int base = p0; base < p1; base += LB) {
+                double v[LB];
+#pragma unroll
+                for (int u = 0; u < LB; ++u) v[u] = (base + u < p1) ? dots2p[(long)(base + u) * S + slot] : 0.0;
+#pragma unroll
+                for (int u = 0; u < LB; ++u) a2 += v[u];
+            }
             s_part[part][slot] = a2;
         }
     }
     __syncthreads();
     if (t < S && (t <= k || (t >= nb && t < nb + k) || t == 2 * nb)) {
         double a2 = 0.0;
-#pragma unroll
-        for (int pz = 0; pz < 7; ++pz) a2 += s_part[pz][t];
+        for (int pz = 0; pz < TPE; ++pz) a2 += s_part[pz][t];
         s_d[t] = a2;
     }
     __syncthreads();

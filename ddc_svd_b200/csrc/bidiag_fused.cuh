@@ -261,21 +261,33 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
     //      the panel-row area is still unused and serves as scratch (the tiles may already be in flight)
     {
         constexpr int S1 = 2 * NBMAX + 2;
-        double *s_part = qrow, *s_d1 = qrow + 5 * S1;
+        // TPE threads per entry, each adding a contiguous chunk of the partials with all of its loads
+        // in flight at once (a plain accumulate loop serialises one L2 round trip per few partials)
         const int ne = 2 * k + 1;                         // [0..k) V^T c, [nb..nb+k) X^T c, [2nb] c.c
+        const int TPE = (ne <= 65) ? 10 : 5;              // 704 threads: 65 x 10 or 129 x 5
+        double *s_part = qrow, *s_d1 = qrow + 10 * S1;
         if (a.nparts1 > 0) {
-            const int e = tid / 5, part = tid - 5 * e;    // 5 threads per entry (672/5 = 134 >= 129)
+            const int e = tid / TPE, part = tid - TPE * e;
             if (e < ne) {
                 const int slot = (e < k) ? e : (e < 2 * k ? nb + (e - k) : 2 * nb);
-                const int chunk = (a.nparts1 + 4) / 5, p0 = part * chunk, p1 = min(a.nparts1, p0 + chunk);
+                const int chunk = (a.nparts1 + TPE - 1) / TPE, p0 = part * chunk, p1 = min(a.nparts1, p0 + chunk);
+                constexpr int LB = 13;
                 double a2 = 0.0;
-                for (int pz = p0; pz < p1; ++pz) a2 += a.dots1[(long)pz * S1 + slot];
+                for (int base = p0; base < p1; base += LB) {
+                    double v[LB];
+#pragma unroll
+                    for (int u = 0; u < LB; ++u) v[u] = (base + u < p1) ? a.dots1[(long)(base + u) * S1 + slot] : 0.0;
+#pragma unroll
+                    for (int u = 0; u < LB; ++u) a2 += v[u];
+                }
                 s_part[part * S1 + slot] = a2;
             }
             __syncthreads();
-            if (tid < S1 && (tid < k || (tid >= nb && tid < nb + k) || tid == 2 * nb))
-                s_d1[tid] = ((s_part[tid] + s_part[S1 + tid]) + (s_part[2 * S1 + tid] + s_part[3 * S1 + tid])) +
-                            s_part[4 * S1 + tid];
+            if (tid < S1 && (tid < k || (tid >= nb && tid < nb + k) || tid == 2 * nb)) {
+                double a2 = 0.0;
+                for (int pz = 0; pz < TPE; ++pz) a2 += s_part[pz * S1 + tid];
+                s_d1[tid] = a2;
+            }
         } else {
             if (tid < S1 && (tid < k || (tid >= nb && tid < nb + k) || tid == 2 * nb)) s_d1[tid] = a.dots1[tid];
         }
