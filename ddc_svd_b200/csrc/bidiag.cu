@@ -903,17 +903,26 @@ void bidiag_device(int m, int n, double *A, long lda, double *alpha, double *bet
                     fprintf(stderr, "\n");
                 }
             }
-            if (Lb > 4096) {
-                const int nRowBlk = ceil_div(Lb, 128), nColBlk = ceil_div(R, 1024);
-                launch_finish_xf<4>(nRowBlk + nColBlk, st, A, lda, i, m, n, k, nb, b.P, b.ldp, b.Q, b.ldq, b.c,
-                                    (const double *)b.rv, (const double *)b.tmpN, lda, pl.NC,
-                                    (const double *)b.dots2p, pl.NC, beta, nRowBlk, b.dots1p);
-                dots1_parts = nRowBlk;
-            } else {
-                const int nRowBlk = ceil_div(Lb, 32), nColBlk = ceil_div(R, 1024);
-                launch_finish_xf<1>(nRowBlk + nColBlk, st, A, lda, i, m, n, k, nb, b.P, b.ldp, b.Q, b.ldq, b.c,
-                                    (const double *)b.rv, (const double *)b.tmpN, lda, pl.NC,
-                                    (const double *)b.dots2p, pl.NC, beta, nRowBlk, b.dots1p);
+            // rows per CTA = 32 * RB: the smallest RB that keeps the row blocks within one wave
+            // (one 1024-thread CTA per SM); the RB row groups of a CTA run one after the other
+            {
+                const int nColBlk = ceil_div(R, 1024);
+                static const int old_rule = getenv("SVD_GPU_XF_OLD") ? 1 : 0;      // experiments
+                const int rb = old_rule ? (Lb > 4096 ? 4 : 1)
+                                        : (Lb <= 32 * (nsm - nColBlk)) ? 1 : (Lb <= 64 * (nsm - nColBlk)) ? 2 : 4;
+                const int nRowBlk = ceil_div(Lb, 32 * rb);
+                if (rb == 1)
+                    launch_finish_xf<1>(nRowBlk + nColBlk, st, A, lda, i, m, n, k, nb, b.P, b.ldp, b.Q, b.ldq, b.c,
+                                        (const double *)b.rv, (const double *)b.tmpN, lda, pl.NC,
+                                        (const double *)b.dots2p, pl.NC, beta, nRowBlk, b.dots1p);
+                else if (rb == 2)
+                    launch_finish_xf<2>(nRowBlk + nColBlk, st, A, lda, i, m, n, k, nb, b.P, b.ldp, b.Q, b.ldq, b.c,
+                                        (const double *)b.rv, (const double *)b.tmpN, lda, pl.NC,
+                                        (const double *)b.dots2p, pl.NC, beta, nRowBlk, b.dots1p);
+                else
+                    launch_finish_xf<4>(nRowBlk + nColBlk, st, A, lda, i, m, n, k, nb, b.P, b.ldp, b.Q, b.ldq, b.c,
+                                        (const double *)b.rv, (const double *)b.tmpN, lda, pl.NC,
+                                        (const double *)b.dots2p, pl.NC, beta, nRowBlk, b.dots1p);
                 dots1_parts = nRowBlk;
             }
             SVD_KERNEL_CHECK();

@@ -1,0 +1,26 @@
+"""Small end-to-end calls for compute-sanitizer (not a pytest file):
+    compute-sanitizer --tool memcheck python tests/sanitize_target.py
+Covers the fused pass (clusters of 1 and 2 via SVD_GPU_FUSED_CS), the split passes, QR first, the
+wide-as-transpose route, values only, and the phase entry points."""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import util
+import ddc_svd_b200 as D
+
+EPS = 2.220446049250313e-16
+for (m, n) in [(300, 300), (700, 120), (120, 700), (513, 257), (64, 64), (1, 1), (2, 5)]:
+    A = util.rand_matrix(m, n)
+    s, U, V, _ = D.svd_gpu(A)
+    met = util.svd_metrics(A, s, U, V)
+    assert met["resid"] <= 100 * EPS * max(m, n), (m, n, met)
+    s2, _, _, _ = D.svd_gpu(A, vectors=False)
+    assert np.abs(s2 - s).max() <= 10 * EPS * max(m, n) * max(s.max(), 1.0)
+    print("svd_gpu", (m, n), "ok", flush=True)
+A = util.rand_matrix(400, 350)
+Am, al, be = D.bidiag_par(A)
+Ao, ao, bo = util.oracle_bidiag(A)
+assert np.abs(Am - Ao).max() <= 1e-9
+Aq, R, Q1 = D.qr_tall(util.rand_matrix(900, 130))
+print("phases ok", flush=True)
