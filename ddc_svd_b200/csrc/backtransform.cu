@@ -155,7 +155,7 @@ void wy_apply_device(int left, int rows, int nref, const double *A, long lda, do
         const double *VTp = VT + r0 + (long)p * NBW * ld;
         int tiles = ceil_div(nc, 64) * ceil_div(NBW, 128);
         int split = 1;
-        if (tiles < 2 * nsm) {
+        if (tiles < 2 * nsm) {                  // (3x / 4x / 6x the SM count measured the same)
             split = (2 * nsm) / tiles;
             int maxs = K / 256;                 // at least 256 of K per slice
             if (split > maxs) split = maxs;

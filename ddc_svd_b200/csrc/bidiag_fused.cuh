@@ -51,8 +51,8 @@ constexpr int FZ_THREADS = FZ_WARPS * 32;
 constexpr int FZ_MAXCS = 8;               // largest cluster
 constexpr int FZ_MAX_CLUSTERS = 148;
 constexpr bool FZ_DEFAULT_ON = true;      // measured faster than the split passes at 4096^2 and 16384^2 (profiles/)
-constexpr int FZ_MIN_ROWS = 128;          // below this trailing height the split passes are used (measured crossover)
-constexpr int FZ_MIN_COLS = 32;
+constexpr int FZ_MIN_ROWS = 16;           // below this trailing height / width the split passes are used (measured:
+constexpr int FZ_MIN_COLS = 8;            //  with dependent launch the fused step wins down to a handful of rows)
 
 constexpr size_t FZ_SMEM_DOUBLES = (size_t)FZ_STAGES * FZ_STAGE                      // tiles
                                    + (size_t)FZ_STAGES * FZ_CBW_MAX * 2 * NBMAX      // panel rows of the tile columns
