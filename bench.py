@@ -331,6 +331,7 @@ def run_own(args):
                 "kernel": ("fused_pass_kernel (single-read pass; gemvT/gemvN below 128 rows) + finish_xf + panel GEMM"
                            if fused_on else "gemvT_kernel + gemvN_kernel + finish_y/x + panel GEMM"),
                 "achieved": ach_survey, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach_survey / pk["hbm_gbs"],
+                "frac_of_8000_nominal": ach_survey / 8000.0,
                 "traffic": NCU_TRAFFIC.get(n), "traffic_note": NCU_TRAFFIC_NOTE,
                 "definition": "achieved = SURVEY 8(d) B_alg (12*S bytes: unblocked 3-transfer scheme) / bidiag phase "
                               "time from CUDA events (all bidiag launches); can exceed 1.0 because the panel-deferred "
@@ -346,7 +347,9 @@ def run_own(args):
 
     # ---- e2e: the reference-facing call with pinned host buffers, copies inside the timed region
     e2e = None
-    if world == 1:
+    if args.no_e2e:
+        pass
+    elif world == 1:
         nbytes = m * n * 8
         pin = [L.svdgpu_host_alloc(nbytes) for _ in range(3)]
         pin_sig = L.svdgpu_host_alloc(mn * 8)
@@ -442,6 +445,8 @@ def main():
     ap.add_argument("--size", "--n", dest="n", type=int, default=int(os.environ.get("SVD_BENCH_N", "4096")))
     ap.add_argument("--cpu-n", type=int, default=1024, help="size of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true",
+                    help="skip the end-to-end leg (single-shot runs of the largest configs; e2e is then null)")
     ap.add_argument("--check", action="store_true", help="verify the last step's result against LAPACK (n <= 8192)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
