@@ -74,6 +74,32 @@ __global__ void __launch_bounds__(NBW) wy_tinv_kernel(const double *__restrict__
     }
 }
 
+// K split of the long-K products W = V^T C (few output tiles, K = the reflector length).
+// One-tile-per-CTA kernel: fill the 2 x nsm CTA slots (3x / 4x / 6x the SM count measured the same).
+// Persistent kernel (dgemm_ws.cu): its CTAs walk tiles x slices round-robin, so the smallest split that
+// leaves the last round at least 95 % full (else the fullest one); at least 256 of K per slice.
+static int pick_split(int tiles, int K, int nsm)
+{
+    int maxs = K / 256;
+    if (maxs > WY_MAX_SPLIT) maxs = WY_MAX_SPLIT;
+    if (maxs < 1) maxs = 1;
+    if (!dgemm_ws_enabled()) {
+        int split = 1;
+        if (tiles < 2 * nsm) split = (2 * nsm) / tiles;
+        if (split > maxs) split = maxs;
+        return split < 1 ? 1 : split;
+    }
+    int best = 1;
+    double best_eff = 0.0;
+    for (int sp = 1; sp <= maxs; ++sp) {
+        const long units = (long)tiles * sp;
+        const double eff = (double)units / (double)((units + nsm - 1) / nsm * nsm);
+        if (eff >= 0.95) return sp;
+        if (eff > best_eff + 1e-9) { best_eff = eff; best = sp; }
+    }
+    return best;
+}
+
 size_t backtransform_workspace_bytes(int rows, int nref, int nc)
 {
     long ld = round_up(rows, 2);
@@ -153,15 +179,7 @@ void wy_apply_device(int left, int rows, int nref, const double *A, long lda, do
         if (K <= 0) continue;
         const double *Vp = V + r0 + (long)p * NBW * ld;
         const double *VTp = VT + r0 + (long)p * NBW * ld;
-        int tiles = ceil_div(nc, 64) * ceil_div(NBW, 128);
-        int split = 1;
-        if (tiles < 2 * nsm) {                  // (3x / 4x / 6x the SM count measured the same)
-            split = (2 * nsm) / tiles;
-            int maxs = K / 256;                 // at least 256 of K per slice
-            if (split > maxs) split = maxs;
-            if (split > WY_MAX_SPLIT) split = WY_MAX_SPLIT;
-            if (split < 1) split = 1;
-        }
+        const int split = pick_split(ceil_div(nc, 64) * ceil_div(NBW, 128), K, nsm);
         GemmArgs g1 = {};
         g1.M = NBW; g1.N = nc; g1.K = K;
         g1.A = Vp; g1.lda = ld; g1.transA = 1;
@@ -428,14 +446,7 @@ void qr_device(int m, int n, double *A, long lda, double *R, long ldr, void *wor
         g2.C = VTt; g2.ldc = ldv; g2.alpha = 1.0; g2.beta = 0.0; g2.batch = 1; g2.splitk = 1;
         dgemm_dmma(g2, st);
         double *A2 = A + p0 + (long)(p0 + pw) * lda;
-        int tiles = ceil_div(ntrail, 64), split = 1;
-        if (tiles < 2 * nsm) {
-            split = (2 * nsm) / tiles;
-            int maxs = rows / 256;
-            if (split > maxs) split = maxs;
-            if (split > WY_MAX_SPLIT) split = WY_MAX_SPLIT;
-            if (split < 1) split = 1;
-        }
+        const int split = pick_split(ceil_div(ntrail, 64), rows, nsm);
         GemmArgs g3 = {};
         g3.M = NBW; g3.N = ntrail; g3.K = rows; g3.A = Vp; g3.lda = ldv; g3.transA = 1; g3.B = A2; g3.ldb = lda; g3.transB = 0;
         g3.alpha = 1.0; g3.beta = 0.0; g3.batch = 1;

@@ -27,6 +27,8 @@
 namespace svdgpu {
 
 constexpr int NBMAX = 64;
+constexpr int NB_BIG_DEFAULT = 0;          // > 0: panel width while the trailing block is large (see bidiag_device)
+constexpr int NB_BIG_MIN_DEFAULT = 6144;   // trailing rows/columns from which NB_BIG is used
 constexpr int GT_CW = 4;          // columns per warp in gemvT
 constexpr int GT_WARPS = 8;
 constexpr int GN_THREADS = 256;   // each thread owns 2 rows in gemvN
@@ -848,6 +850,19 @@ void bidiag_device(int m, int n, double *A, long lda, double *alpha, double *bet
     const int fz_min_rows = e1 ? atoi(e1) : FZ_MIN_ROWS, fz_min_cols = e2 ? atoi(e2) : FZ_MIN_COLS;
     bool dots1_ready = false;       // dots1p holds dots1_parts partial dot vectors of the current column c
     int dots1_parts = 0;
+    // Panel width schedule.  The deferred trailing update is a K = 2nb GEMM that reads and writes the
+    // trailing block once per panel: with nb = 32 it is bound by that C traffic and by per-tile
+    // latency, with nb = 64 by the DMMA pipe.  The per-step panel corrections grow with nb, which only
+    // pays while the trailing block is large: panels that start with >= nb_big_min trailing rows and
+    // columns use nb_big, later ones the caller's nb.  (The panel buffers are sized for NBMAX.)
+    const int nb_small = nb;
+    int nb_big = nb, nb_big_min = 1 << 30;
+    {
+        const char *eb = getenv("SVD_GPU_NB_BIG"), *em = getenv("SVD_GPU_NB_BIG_MIN");
+        if (eb) { nb_big = atoi(eb); nb_big_min = em ? atoi(em) : NB_BIG_MIN_DEFAULT; }
+        else if (NB_BIG_DEFAULT > 0 && nb == 32) { nb_big = NB_BIG_DEFAULT; nb_big_min = em ? atoi(em) : NB_BIG_MIN_DEFAULT; }
+        if (nb_big <= 0 || nb_big > NBMAX) nb_big = nb;
+    }
 
     SVD_CUDA_CHECK(cudaMemsetAsync(b.rv, 0, sizeof(double) * ((size_t)b.ldq + 2), st));
     SVD_CUDA_CHECK(cudaMemsetAsync(b.dots1, 0, sizeof(double) * 2 * DOT_SLOTS, st));
@@ -858,6 +873,12 @@ void bidiag_device(int m, int n, double *A, long lda, double *alpha, double *bet
     int k = 0;
     for (int i = 0; i < mn; ++i) {              // steps 0..mn-2 regular, step mn-1 is the tail
         const bool tail = (i == mn - 1);
+        if (k == 0) {
+            const int nb_next = (m - i >= nb_big_min && n - i >= nb_big_min) ? nb_big : nb_small;
+            // the dot slots finish_xf left for this step are laid out for the previous panel's width
+            if (nb_next != nb) dots1_ready = false;
+            nb = nb_next;
+        }
         const int do_col = tail ? (n >= m + 1 ? 0 : 1) : 1;
         const int do_row = tail ? (n >= m + 1 ? 1 : 0) : (i < n - 2 ? 1 : 0);
         const int R = n - i - 1, Lb = m - i - 1;

@@ -209,8 +209,19 @@ static void launch_cfg(const GemmArgs &g, cudaStream_t st)
 
 template <bool TA, bool TB> static void launch_t(const GemmArgs &g, cudaStream_t st)
 {
-    if (g.M > 64) launch_cfg<128, 64, TA, TB>(g, st);
+    // SVD_GPU_GEMM_TILE=64 (experiments): 64 x 64 tiles, 4 CTAs of 4 warps per SM instead of 2 of 8
+    const char *te = getenv("SVD_GPU_GEMM_TILE");
+    const bool force64 = te && atoi(te) == 64;
+    if (g.M > 64 && !force64) launch_cfg<128, 64, TA, TB>(g, st);
     else launch_cfg<64, 64, TA, TB>(g, st);
+}
+
+// SVD_GPU_GEMM_WS=0/1 overrides the default choice between the one-tile-per-CTA kernel of this file
+// and the persistent warp-specialised kernel of dgemm_ws.cu (read on every call: tests flip it)
+bool dgemm_ws_enabled()
+{
+    const char *e = getenv("SVD_GPU_GEMM_WS");
+    return e ? (e[0] != '0') : (DGEMM_WS_DEFAULT != 0);
 }
 
 void dgemm_dmma(const GemmArgs &gin, cudaStream_t st)
@@ -219,6 +230,7 @@ void dgemm_dmma(const GemmArgs &gin, cudaStream_t st)
     if (g.batch < 1) g.batch = 1;
     if (g.splitk < 1) g.splitk = 1;
     if (g.M <= 0 || g.N <= 0) return;
+    if (dgemm_ws_enabled() && dgemm_ws_eligible(g)) { dgemm_ws(g, st); return; }
     if (g.transA) { if (g.transB) launch_t<true, true>(g, st); else launch_t<true, false>(g, st); }
     else          { if (g.transB) launch_t<false, true>(g, st); else launch_t<false, false>(g, st); }
 }

@@ -1,0 +1,323 @@
+// dgemm_ws.cu — persistent, warp-specialised FP64 GEMM on the sm_100a DMMA pipe.
+//
+// Same contract as dgemm_dmma_kernel (dgemm_dmma.cu) for the two shapes that carry the BLAS3 work of
+// the svd_gpu() path — the compact-WY back-transform that replaces multU / multV
+// (bidiag_par.c:990-1095, svd_gpu.c:117-121) and the deferred rank-2nb update of the panel
+// bidiagonalization (left_update_mat.cl / right_update_mat.cl applied once per panel):
+//   * C -= A*B with a short K (64..128): per 128 x 64 tile the DMMA work is only a few microseconds,
+//     so in the one-tile-per-CTA kernel the read of the C tile and the pipeline fill are exposed once
+//     per tile (ncu: a third of the stall samples on the first use of the C tile);
+//   * W = V^T C with a long K and few output tiles: 256 tiles on 2 x 148 CTA slots leave 14 % of the
+//     slots empty.
+// Here one CTA per SM stays resident and walks work units (tile x K-slice) round-robin:
+//   warps 0-7   consumers: 32 x 32 warp tiles (4 x 4 DMMA.8x8x4 fragments), accumulators start from the
+//               C tile that was staged in shared memory while the previous tile was being computed,
+//               results go from registers straight to global memory;
+//   warps 8-11  producers: cp.async (zero-filled at the edges, any alignment) of the A/B stages and of
+//               the NEXT unit's C tile, completion signalled through mbarriers
+//               (cp.async.mbarrier.arrive.noinc), so the consumers never issue or wait for a global load.
+// Stages are handed back by one elected lane per consumer warp.  No CTA-wide barrier after set-up.
+#include "common.cuh"
+
+namespace svdgpu {
+
+namespace {
+
+constexpr int WS_BM = 128, WS_BN = 64, WS_BK = 16, WS_STAGES = 4;
+constexpr int WS_CONS_WARPS = 8, WS_PROD_WARPS = 4;
+constexpr int WS_CONS = WS_CONS_WARPS * 32, WS_PROD = WS_PROD_WARPS * 32;
+constexpr int WS_THREADS = WS_CONS + WS_PROD;
+constexpr int WS_LDC_S = WS_BM + 2;       // 2*tq*130 + gq: the accumulator loads of a half-warp hit 16 distinct banks
+
+template <bool TA, bool TB> struct WsCfg {
+    static constexpr int LDA_S = TA ? (WS_BK + 4) : (WS_BM + 4);
+    static constexpr int LDB_S = TB ? (WS_BN + 4) : (WS_BK + 4);
+    static constexpr int A_ELEMS = TA ? WS_BM * LDA_S : WS_BK * LDA_S;
+    static constexpr int B_ELEMS = TB ? WS_BK * LDB_S : WS_BN * LDB_S;
+    static constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS;
+    static constexpr int C_ELEMS = WS_BN * WS_LDC_S;
+    static constexpr int NBAR = 2 * WS_STAGES + 2;
+    static constexpr size_t SMEM_BYTES = (size_t)(WS_STAGES * STAGE_ELEMS + C_ELEMS) * 8 + NBAR * 8 + 16;
+};
+
+__device__ __forceinline__ unsigned ws_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ws_mbar_init(uint64_t *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ws_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void ws_mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ws_u32(bar)) : "memory");
+}
+// arrive once all cp.async issued so far by this thread have landed (the barrier's expected count
+// already includes this arrival: .noinc)
+__device__ __forceinline__ void ws_cp_async_arrive(uint64_t *bar)
+{
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(ws_u32(bar)) : "memory");
+}
+// wait for the phase with the given parity; a wait that lasts longer than ~2 s of SM clocks is a
+// protocol bug: trap instead of hanging the device
+__device__ __forceinline__ void ws_mbar_wait(uint64_t *bar, unsigned parity)
+{
+    const unsigned a = ws_u32(bar);
+    unsigned ok = 0;
+    long long t0 = 0;
+    for (int spin = 0;; ++spin) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (ok) return;
+        if (spin == 64) t0 = clock64();
+        if (spin > 64 && (spin & 1023) == 0 && clock64() - t0 > 4000000000ll) {
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void ws_cp_async8(void *smem, const void *gmem, bool valid)
+{
+    const int bytes = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(ws_u32(smem)), "l"(gmem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ws_dmma884(double &d0, double &d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+struct WsUnit { int m0, n0, kbeg, kend, zs; };
+
+// unit u -> tile (m fastest, so that neighbouring CTAs share the B tile in L2) and K slice
+__device__ __forceinline__ WsUnit ws_unit(const GemmArgs &g, int u, int tilesM, int ntiles)
+{
+    WsUnit w;
+    w.zs = u / ntiles;
+    const int t = u - w.zs * ntiles;
+    const int tn = t / tilesM;
+    w.m0 = (t - tn * tilesM) * WS_BM;
+    w.n0 = tn * WS_BN;
+    w.kbeg = 0; w.kend = g.K;
+    if (g.splitk > 1) {
+        const int chunk = ((g.K + g.splitk - 1) / g.splitk + WS_BK - 1) / WS_BK * WS_BK;
+        w.kbeg = w.zs * chunk;
+        w.kend = min(g.K, w.kbeg + chunk);
+    }
+    return w;
+}
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(WS_THREADS, 1)
+dgemm_ws_kernel(GemmArgs g, int tilesM, int ntiles, int nunits)
+{
+    using Cfg = WsCfg<TA, TB>;
+    extern __shared__ __align__(16) double smem[];
+    double *Cs = smem + WS_STAGES * Cfg::STAGE_ELEMS;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(Cs + Cfg::C_ELEMS);
+    uint64_t *full = bars, *empty = bars + WS_STAGES, *cfull = bars + 2 * WS_STAGES, *cempty = cfull + 1;
+
+    const int tid = threadIdx.x;
+    // accumulators start from C (alpha = +-1, beta != 0, no K split), else from zero with beta == 0
+    const bool has_c = (g.splitk <= 1) && (g.beta != 0.0);
+    if (tid == 0) {
+        for (int s = 0; s < WS_STAGES; ++s) { ws_mbar_init(full + s, WS_PROD); ws_mbar_init(empty + s, WS_CONS_WARPS); }
+        ws_mbar_init(cfull, WS_PROD);
+        ws_mbar_init(cempty, WS_CONS_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (tid >= WS_CONS) {
+        // ------------------------------------------------------------------ producers
+        const int p = tid - WS_CONS;                       // 0..127
+        auto load_c = [&](const WsUnit &w) {
+            const bool rok = (w.m0 + p < g.M);
+            const double *src = g.C + (w.m0 + p) + (long)w.n0 * g.ldc;
+#pragma unroll 8
+            for (int j = 0; j < WS_BN; ++j) {
+                const bool ok = rok && (w.n0 + j < g.N);
+                ws_cp_async8(Cs + j * WS_LDC_S + p, ok ? src + (long)j * g.ldc : g.C, ok);
+            }
+        };
+        unsigned it = 0, tl = 0;
+        for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++tl) {
+            const WsUnit w = ws_unit(g, u, tilesM, ntiles);
+            const int nk = (w.kend > w.kbeg) ? (w.kend - w.kbeg + WS_BK - 1) / WS_BK : 0;
+            if (has_c && tl == 0) { load_c(w); ws_cp_async_arrive(cfull); }
+            const int cpoint = (nk < WS_STAGES ? nk : WS_STAGES) - 1;      // after this k-step: stage the next C tile
+            for (int kt = 0; kt < nk; ++kt, ++it) {
+                const unsigned stage = it % WS_STAGES, fill = it / WS_STAGES;
+                ws_mbar_wait(empty + stage, (fill & 1u) ^ 1u);
+                double *As = smem + stage * Cfg::STAGE_ELEMS;
+                double *Bs = As + Cfg::A_ELEMS;
+                const int k0 = w.kbeg + kt * WS_BK;
+                if (!TA) {          // A is M x K, m contiguous -> As[k][m]; this thread owns row p of the tile
+                    const bool rok = (w.m0 + p < g.M);
+                    const double *src = g.A + (w.m0 + p) + (long)k0 * g.lda;
+#pragma unroll
+                    for (int kk = 0; kk < WS_BK; ++kk) {
+                        const bool ok = rok && (k0 + kk < w.kend);
+                        ws_cp_async8(As + kk * Cfg::LDA_S + p, ok ? src + (long)kk * g.lda : g.A, ok);
+                    }
+                } else {            // A stored K x M, k contiguous -> As[m][k]
+                    const int kk = p & 15, mb = p >> 4;
+                    const bool kok = (k0 + kk < w.kend);
+#pragma unroll
+                    for (int j = 0; j < WS_BM / 8; ++j) {
+                        const int mm = mb + 8 * j;
+                        const bool ok = kok && (w.m0 + mm < g.M);
+                        ws_cp_async8(As + mm * Cfg::LDA_S + kk, ok ? g.A + (k0 + kk) + (long)(w.m0 + mm) * g.lda : g.A, ok);
+                    }
+                }
+                if (!TB) {          // B is K x N, k contiguous -> Bs[n][k]
+                    const int kk = p & 15, nb0 = p >> 4;
+                    const bool kok = (k0 + kk < w.kend);
+#pragma unroll
+                    for (int j = 0; j < WS_BN / 8; ++j) {
+                        const int nn = nb0 + 8 * j;
+                        const bool ok = kok && (w.n0 + nn < g.N);
+                        ws_cp_async8(Bs + nn * Cfg::LDB_S + kk, ok ? g.B + (k0 + kk) + (long)(w.n0 + nn) * g.ldb : g.B, ok);
+                    }
+                } else {            // B stored N x K, n contiguous -> Bs[k][n]
+                    const int nn = p & 63, kb = p >> 6;
+                    const bool nok = (w.n0 + nn < g.N);
+#pragma unroll
+                    for (int j = 0; j < WS_BK / 2; ++j) {
+                        const int kk = kb + 2 * j;
+                        const bool ok = nok && (k0 + kk < w.kend);
+                        ws_cp_async8(Bs + kk * Cfg::LDB_S + nn, ok ? g.B + (w.n0 + nn) + (long)(k0 + kk) * g.ldb : g.B, ok);
+                    }
+                }
+                ws_cp_async_arrive(full + stage);
+                if (has_c && kt == cpoint) {
+                    const int un = u + gridDim.x;
+                    if (un < nunits) {
+                        // the consumers hand the C buffer back as soon as this unit's accumulators are loaded
+                        ws_mbar_wait(cempty, (tl & 1u));
+                        load_c(ws_unit(g, un, tilesM, ntiles));
+                        ws_cp_async_arrive(cfull);
+                    }
+                }
+            }
+            if (has_c && nk == 0) {                        // degenerate K: still keep the C hand-over in step
+                const int un = u + gridDim.x;
+                if (un < nunits) {
+                    ws_mbar_wait(cempty, (tl & 1u));
+                    load_c(ws_unit(g, un, tilesM, ntiles));
+                    ws_cp_async_arrive(cfull);
+                }
+            }
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        return;
+    }
+
+    // ---------------------------------------------------------------------- consumers
+    const int lane = tid & 31, warp = tid >> 5;
+    const int gq = lane >> 2, tq = lane & 3;
+    const int wm0 = (warp & 3) * 32, wn0 = (warp >> 2) * 32;
+    const double sc = has_c ? g.beta * g.alpha : 0.0;      // beta/alpha for alpha = +-1
+    unsigned it = 0, tl = 0;
+    for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++tl) {
+        const WsUnit w = ws_unit(g, u, tilesM, ntiles);
+        const int nk = (w.kend > w.kbeg) ? (w.kend - w.kbeg + WS_BK - 1) / WS_BK : 0;
+        double acc[4][4][2];
+        if (has_c) {
+            ws_mbar_wait(cfull, tl & 1u);
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+                        acc[mi][ni][e] = sc * Cs[(wn0 + ni * 8 + 2 * tq + e) * WS_LDC_S + wm0 + mi * 8 + gq];
+            __syncwarp();
+            if (lane == 0) ws_mbar_arrive(cempty);
+        } else {
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+        }
+        for (int kt = 0; kt < nk; ++kt, ++it) {
+            const unsigned stage = it % WS_STAGES, fill = it / WS_STAGES;
+            ws_mbar_wait(full + stage, fill & 1u);
+            const double *As = smem + stage * Cfg::STAGE_ELEMS;
+            const double *Bs = As + Cfg::A_ELEMS;
+#pragma unroll
+            for (int k4 = 0; k4 < WS_BK / 4; ++k4) {
+                double a[4], b[4];
+                const int kk = k4 * 4 + tq;
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi) {
+                    const int mm = wm0 + mi * 8 + gq;
+                    a[mi] = TA ? As[mm * Cfg::LDA_S + kk] : As[kk * Cfg::LDA_S + mm];
+                }
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) {
+                    const int nn = wn0 + ni * 8 + gq;
+                    b[ni] = TB ? Bs[kk * Cfg::LDB_S + nn] : Bs[nn * Cfg::LDB_S + kk];
+                }
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni) ws_dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+            }
+            __syncwarp();
+            if (lane == 0) ws_mbar_arrive(empty + stage);
+        }
+        // epilogue: registers -> global (has_c: the accumulators already hold beta/alpha * C)
+        double *C = g.C + (g.splitk > 1 ? (long)w.zs * g.sSplit : 0);
+        const double alpha = g.alpha;
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) {
+            const int mm = w.m0 + wm0 + mi * 8 + gq;
+            if (mm >= g.M) continue;
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int nn = w.n0 + wn0 + ni * 8 + 2 * tq + e;
+                    if (nn < g.N) C[mm + (long)nn * g.ldc] = alpha * acc[mi][ni][e];
+                }
+        }
+    }
+}
+
+template <bool TA, bool TB> void launch_ws(const GemmArgs &g, cudaStream_t st)
+{
+    using Cfg = WsCfg<TA, TB>;
+    static int nsm = 0;
+    int dev = 0;
+    SVD_CUDA_CHECK(cudaGetDevice(&dev));
+    if (nsm == 0) SVD_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    // per-device attribute; cheap enough to set on every launch (multi-GPU safe)
+    SVD_CUDA_CHECK(cudaFuncSetAttribute(dgemm_ws_kernel<TA, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)Cfg::SMEM_BYTES));
+    const int tilesM = ceil_div(g.M, WS_BM), tilesN = ceil_div(g.N, WS_BN);
+    const int ntiles = tilesM * tilesN, nunits = ntiles * g.splitk;
+    const int grid = nunits < nsm ? nunits : nsm;
+    dgemm_ws_kernel<TA, TB><<<grid, WS_THREADS, Cfg::SMEM_BYTES, st>>>(g, tilesM, ntiles, nunits);
+    SVD_KERNEL_CHECK();
+}
+
+} // namespace
+
+// Shapes the persistent kernel takes over (the rest stays with dgemm_dmma_kernel): one batch entry,
+// either a pure product (beta == 0, K split allowed) or an update C = beta*C +- A*B without a K split.
+bool dgemm_ws_eligible(const GemmArgs &g)
+{
+    if (g.batch > 1 || g.M <= 64 || g.N <= 0 || g.K <= 0) return false;
+    if (g.splitk > 1) return true;                         // slices are pure products (beta ignored)
+    if (g.beta == 0.0) return true;
+    return g.alpha == 1.0 || g.alpha == -1.0;
+}
+
+void dgemm_ws(const GemmArgs &g, cudaStream_t st)
+{
+    if (g.transA) { if (g.transB) launch_ws<true, true>(g, st); else launch_ws<true, false>(g, st); }
+    else          { if (g.transB) launch_ws<false, true>(g, st); else launch_ws<false, false>(g, st); }
+}
+
+} // namespace svdgpu

@@ -347,10 +347,13 @@ def test_svd_gpu_vs_oracle_512(D):
 @pytest.mark.parametrize("case", [(0, 0, 130, 70, 50), (1, 0, 64, 200, 333), (0, 1, 257, 129, 64), (1, 1, 65, 66, 67),
                                   (0, 1, 1000, 900, 64), (0, 0, 700, 513, 128), (0, 1, 256, 256, 16),
                                   (0, 0, 1531, 777, 100), (0, 1, 4100, 300, 64)])
-@pytest.mark.parametrize("alpha_beta", [(-1.0, 1.0), (1.0, 1.0), (0.5, 0.0)])
-def test_dgemm_vs_numpy(D, case, alpha_beta):
-    # (transA, transB, M, N, K); alpha = +-1 with beta = 1 and M, N >= 256 takes the persistent
-    # rank-K update kernel, everything else the generic one
+@pytest.mark.parametrize("alpha_beta", [(-1.0, 1.0), (1.0, 1.0), (0.5, 0.0), (0.5, 2.0)])
+@pytest.mark.parametrize("ws", ["0", "1"])
+def test_dgemm_vs_numpy(D, case, alpha_beta, ws, monkeypatch):
+    # (transA, transB, M, N, K).  ws = 1: updates (alpha = +-1, beta != 0) and pure products with M > 64
+    # go to the persistent warp-specialised kernel (dgemm_ws.cu), everything else - and everything
+    # with ws = 0 - to the one-tile-per-CTA kernel (dgemm_dmma.cu)
+    monkeypatch.setenv("SVD_GPU_GEMM_WS", ws)
     ta, tb, M, N, K = case
     alpha, beta = alpha_beta
     L = D.lib()
@@ -373,6 +376,27 @@ def test_dgemm_vs_numpy(D, case, alpha_beta):
             L.svdgpu_free(d)
     ref = beta * C + alpha * (A @ B)
     assert np.abs(out - ref).max() <= 50 * EPS * K * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("shape", [(1500, 1300), (700, 900), (5000, 257), (2048, 2048)])
+def test_svd_gpu_gemm_kernels_agree(D, shape, monkeypatch):
+    # the whole path (panel updates of the bidiagonalization, split-K products and updates of the
+    # back-transform, the QR-first route) with either GEMM kernel: same answer up to summation order
+    m, n = shape
+    A = util.rand_matrix(m, n)
+    out = {}
+    for ws in ("0", "1"):
+        monkeypatch.setenv("SVD_GPU_GEMM_WS", ws)
+        out[ws] = D.svd_gpu(A)
+        check_lapack_bounds(A, *out[ws][:3])
+    s0, U0, V0, _ = out["0"]; s1, U1, V1, _ = out["1"]
+    assert np.abs(s0 - s1).max() <= 50 * EPS * max(m, n) * s0.max()
+    # vectors of well separated singular values agree up to sign
+    gap = np.minimum(np.diff(s0, prepend=-np.inf), np.diff(s0, append=np.inf))
+    sep = gap > 1e-3 * s0.max()
+    if sep.any():
+        assert np.all(np.abs(np.sum(U0[:, sep] * U1[:, sep], axis=0)) >= 1 - 1e-8)
+        assert np.all(np.abs(np.sum(V0[:, sep] * V1[:, sep], axis=0)) >= 1 - 1e-8)
 
 
 # ------------------------------------------------------------------ QR first (m >> n)
