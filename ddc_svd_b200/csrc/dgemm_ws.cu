@@ -23,21 +23,24 @@ namespace svdgpu {
 
 namespace {
 
-constexpr int WS_BM = 128, WS_BN = 64, WS_BK = 16, WS_STAGES = 4;
+constexpr int WS_BM = 128, WS_BN = 64, WS_BK = 16;
 constexpr int WS_CONS_WARPS = 8, WS_PROD_WARPS = 4;
 constexpr int WS_CONS = WS_CONS_WARPS * 32, WS_PROD = WS_PROD_WARPS * 32;
 constexpr int WS_THREADS = WS_CONS + WS_PROD;
 constexpr int WS_LDC_S = WS_BM + 2;       // 2*tq*130 + gq: the accumulator loads of a half-warp hit 16 distinct banks
 
-template <bool TA, bool TB> struct WsCfg {
+// HASC: the accumulators start from a staged C tile (updates): 4 stages + the C buffer.  Pure products
+// (W = V^T C streams its B operand from HBM) get 6 stages and no C buffer instead.
+template <bool TA, bool TB, bool HASC> struct WsCfg {
+    static constexpr int STAGES = HASC ? 4 : 6;
     static constexpr int LDA_S = TA ? (WS_BK + 4) : (WS_BM + 4);
     static constexpr int LDB_S = TB ? (WS_BN + 4) : (WS_BK + 4);
     static constexpr int A_ELEMS = TA ? WS_BM * LDA_S : WS_BK * LDA_S;
     static constexpr int B_ELEMS = TB ? WS_BK * LDB_S : WS_BN * LDB_S;
     static constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS;
-    static constexpr int C_ELEMS = WS_BN * WS_LDC_S;
-    static constexpr int NBAR = 2 * WS_STAGES + 2;
-    static constexpr size_t SMEM_BYTES = (size_t)(WS_STAGES * STAGE_ELEMS + C_ELEMS) * 8 + NBAR * 8 + 16;
+    static constexpr int C_ELEMS = HASC ? WS_BN * WS_LDC_S : 0;
+    static constexpr int NBAR = 2 * STAGES + 2;
+    static constexpr size_t SMEM_BYTES = (size_t)(STAGES * STAGE_ELEMS + C_ELEMS) * 8 + NBAR * 8 + 16;
 };
 
 __device__ __forceinline__ unsigned ws_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -87,6 +90,31 @@ __device__ __forceinline__ void ws_dmma884(double &d0, double &d1, double a, dou
                  : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
+__device__ __forceinline__ void ws_dmma16(double (&acc)[4][4][2], const double (&a)[4], const double (&b)[4])
+{
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) ws_dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+}
+// one non-blocking look at a barrier phase
+__device__ __forceinline__ bool ws_mbar_test(uint64_t *bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(ws_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// -x without the FP64 pipe
+__device__ __forceinline__ double ws_neg(double x)
+{
+    return __hiloint2double(__double2hiint(x) ^ (int)0x80000000, __double2loint(x));
+}
+
 struct WsUnit { int m0, n0, kbeg, kend, zs; };
 
 // unit u -> tile (m fastest, so that neighbouring CTAs share the B tile in L2) and K slice
@@ -107,11 +135,12 @@ __device__ __forceinline__ WsUnit ws_unit(const GemmArgs &g, int u, int tilesM, 
     return w;
 }
 
-template <bool TA, bool TB>
+template <bool TA, bool TB, bool HASC>
 __global__ void __launch_bounds__(WS_THREADS, 1)
 dgemm_ws_kernel(GemmArgs g, int tilesM, int ntiles, int nunits)
 {
-    using Cfg = WsCfg<TA, TB>;
+    using Cfg = WsCfg<TA, TB, HASC>;
+    constexpr int WS_STAGES = Cfg::STAGES;
     extern __shared__ __align__(16) double smem[];
     double *Cs = smem + WS_STAGES * Cfg::STAGE_ELEMS;
     uint64_t *bars = reinterpret_cast<uint64_t *>(Cs + Cfg::C_ELEMS);
@@ -119,7 +148,8 @@ dgemm_ws_kernel(GemmArgs g, int tilesM, int ntiles, int nunits)
 
     const int tid = threadIdx.x;
     // accumulators start from C (alpha = +-1, beta != 0, no K split), else from zero with beta == 0
-    const bool has_c = (g.splitk <= 1) && (g.beta != 0.0);
+    // (decided on the host: an FP64 compare here would queue behind the DMMAs in every producer iteration)
+    constexpr bool has_c = HASC;
     if (tid == 0) {
         for (int s = 0; s < WS_STAGES; ++s) { ws_mbar_init(full + s, WS_PROD); ws_mbar_init(empty + s, WS_CONS_WARPS); }
         ws_mbar_init(cfull, WS_PROD);
@@ -218,6 +248,23 @@ dgemm_ws_kernel(GemmArgs g, int tilesM, int ntiles, int nunits)
     const int gq = lane >> 2, tq = lane & 3;
     const int wm0 = (warp & 3) * 32, wn0 = (warp >> 2) * 32;
     const double sc = has_c ? g.beta * g.alpha : 0.0;      // beta/alpha for alpha = +-1
+    // +-1 scalings are sign flips on the integer pipe: the FP64 pipe belongs to the DMMAs
+    const int smode = (sc == 1.0) ? 1 : (sc == -1.0 ? 2 : 0);
+    const int amode = (g.alpha == 1.0) ? 1 : (g.alpha == -1.0 ? 2 : 0);
+    // fragment loads of sub-step k4 of a stage (8 x LDS.64, conflict-free by the padded leading dimensions)
+    auto frags = [&](const double *As, const double *Bs, int k4, double (&a)[4], double (&b)[4]) {
+        const int kk = k4 * 4 + tq;
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) {
+            const int mm = wm0 + mi * 8 + gq;
+            a[mi] = TA ? As[mm * Cfg::LDA_S + kk] : As[kk * Cfg::LDA_S + mm];
+        }
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+            const int nn = wn0 + ni * 8 + gq;
+            b[ni] = TB ? Bs[kk * Cfg::LDB_S + nn] : Bs[nn * Cfg::LDB_S + kk];
+        }
+    };
     unsigned it = 0, tl = 0;
     for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++tl) {
         const WsUnit w = ws_unit(g, u, tilesM, ntiles);
@@ -231,75 +278,118 @@ dgemm_ws_kernel(GemmArgs g, int tilesM, int ntiles, int nunits)
                 for (int ni = 0; ni < 4; ++ni)
 #pragma unroll
                     for (int e = 0; e < 2; ++e)
-                        acc[mi][ni][e] = sc * Cs[(wn0 + ni * 8 + 2 * tq + e) * WS_LDC_S + wm0 + mi * 8 + gq];
+                        acc[mi][ni][e] = Cs[(wn0 + ni * 8 + 2 * tq + e) * WS_LDC_S + wm0 + mi * 8 + gq];
             __syncwarp();
             if (lane == 0) ws_mbar_arrive(cempty);
+            if (smode != 1) {
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e)
+                            acc[mi][ni][e] = (smode == 2) ? ws_neg(acc[mi][ni][e]) : sc * acc[mi][ni][e];
+            }
         } else {
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
                 for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
         }
-        for (int kt = 0; kt < nk; ++kt, ++it) {
+        // main loop, software-pipelined across sub-steps AND stages: the fragments of the next sub-step
+        // (of the next stage, when that one has already landed) are in flight while the 16 DMMAs of the
+        // current one issue, so a stage boundary costs no LDS round trip
+        double a0[4], b0[4], a1[4], b1[4];
+        if (nk > 0) {
             const unsigned stage = it % WS_STAGES, fill = it / WS_STAGES;
             ws_mbar_wait(full + stage, fill & 1u);
             const double *As = smem + stage * Cfg::STAGE_ELEMS;
+            frags(As, As + Cfg::A_ELEMS, 0, a0, b0);
+        }
+        for (int kt = 0; kt < nk; ++kt, ++it) {
+            const unsigned stage = it % WS_STAGES;
+            const double *As = smem + stage * Cfg::STAGE_ELEMS;
             const double *Bs = As + Cfg::A_ELEMS;
-#pragma unroll
-            for (int k4 = 0; k4 < WS_BK / 4; ++k4) {
-                double a[4], b[4];
-                const int kk = k4 * 4 + tq;
-#pragma unroll
-                for (int mi = 0; mi < 4; ++mi) {
-                    const int mm = wm0 + mi * 8 + gq;
-                    a[mi] = TA ? As[mm * Cfg::LDA_S + kk] : As[kk * Cfg::LDA_S + mm];
-                }
-#pragma unroll
-                for (int ni = 0; ni < 4; ++ni) {
-                    const int nn = wn0 + ni * 8 + gq;
-                    b[ni] = TB ? Bs[kk * Cfg::LDB_S + nn] : Bs[nn * Cfg::LDB_S + kk];
-                }
-#pragma unroll
-                for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-                    for (int ni = 0; ni < 4; ++ni) ws_dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
-            }
+            frags(As, Bs, 1, a1, b1);
+            ws_dmma16(acc, a0, b0);
+            frags(As, Bs, 2, a0, b0);
+            ws_dmma16(acc, a1, b1);
+            frags(As, Bs, 3, a1, b1);
+            ws_dmma16(acc, a0, b0);
+            const bool more = (kt + 1 < nk);
+            const unsigned nstage = (it + 1) % WS_STAGES, nfill = (it + 1) / WS_STAGES;
+            const double *An = smem + nstage * Cfg::STAGE_ELEMS;
+            bool pre = false;
+            if (more) pre = __all_sync(0xffffffffu, ws_mbar_test(full + nstage, nfill & 1u));
+            if (pre) frags(An, An + Cfg::A_ELEMS, 0, a0, b0);
+            ws_dmma16(acc, a1, b1);
             __syncwarp();
             if (lane == 0) ws_mbar_arrive(empty + stage);
+            if (more && !pre) {
+                ws_mbar_wait(full + nstage, nfill & 1u);
+                frags(An, An + Cfg::A_ELEMS, 0, a0, b0);
+            }
         }
         // epilogue: registers -> global (has_c: the accumulators already hold beta/alpha * C)
         double *C = g.C + (g.splitk > 1 ? (long)w.zs * g.sSplit : 0);
-        const double alpha = g.alpha;
+        if (amode != 1) {
 #pragma unroll
-        for (int mi = 0; mi < 4; ++mi) {
-            const int mm = w.m0 + wm0 + mi * 8 + gq;
-            if (mm >= g.M) continue;
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+                        acc[mi][ni][e] = (amode == 2) ? ws_neg(acc[mi][ni][e]) : g.alpha * acc[mi][ni][e];
+        }
+        if (w.m0 + WS_BM <= g.M && w.n0 + WS_BN <= g.N) {
+            // interior tile: no bounds tests, one pointer per column
+            double *cb = C + (w.m0 + wm0 + gq) + (long)(w.n0 + wn0 + 2 * tq) * g.ldc;
 #pragma unroll
             for (int ni = 0; ni < 4; ++ni)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const int nn = w.n0 + wn0 + ni * 8 + 2 * tq + e;
-                    if (nn < g.N) C[mm + (long)nn * g.ldc] = alpha * acc[mi][ni][e];
+                    double *col = cb + (long)(ni * 8 + e) * g.ldc;
+#pragma unroll
+                    for (int mi = 0; mi < 4; ++mi) col[mi * 8] = acc[mi][ni][e];
                 }
+        } else {
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) {
+                const int mm = w.m0 + wm0 + mi * 8 + gq;
+                if (mm >= g.M) continue;
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int nn = w.n0 + wn0 + ni * 8 + 2 * tq + e;
+                        if (nn < g.N) C[mm + (long)nn * g.ldc] = acc[mi][ni][e];
+                    }
+            }
         }
     }
 }
 
-template <bool TA, bool TB> void launch_ws(const GemmArgs &g, cudaStream_t st)
+template <bool TA, bool TB, bool HASC> void launch_ws_c(const GemmArgs &g, cudaStream_t st)
 {
-    using Cfg = WsCfg<TA, TB>;
+    using Cfg = WsCfg<TA, TB, HASC>;
     static int nsm = 0;
     int dev = 0;
     SVD_CUDA_CHECK(cudaGetDevice(&dev));
     if (nsm == 0) SVD_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
     // per-device attribute; cheap enough to set on every launch (multi-GPU safe)
-    SVD_CUDA_CHECK(cudaFuncSetAttribute(dgemm_ws_kernel<TA, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SVD_CUDA_CHECK(cudaFuncSetAttribute(dgemm_ws_kernel<TA, TB, HASC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)Cfg::SMEM_BYTES));
     const int tilesM = ceil_div(g.M, WS_BM), tilesN = ceil_div(g.N, WS_BN);
     const int ntiles = tilesM * tilesN, nunits = ntiles * g.splitk;
     const int grid = nunits < nsm ? nunits : nsm;
-    dgemm_ws_kernel<TA, TB><<<grid, WS_THREADS, Cfg::SMEM_BYTES, st>>>(g, tilesM, ntiles, nunits);
+    dgemm_ws_kernel<TA, TB, HASC><<<grid, WS_THREADS, Cfg::SMEM_BYTES, st>>>(g, tilesM, ntiles, nunits);
     SVD_KERNEL_CHECK();
+}
+
+template <bool TA, bool TB> void launch_ws(const GemmArgs &g, cudaStream_t st)
+{
+    if (g.splitk <= 1 && g.beta != 0.0) launch_ws_c<TA, TB, true>(g, st);
+    else launch_ws_c<TA, TB, false>(g, st);
 }
 
 } // namespace
