@@ -48,20 +48,30 @@ def peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
 
 
-def bidiag_bytes(m, n, nb, fused=True):
+def bidiag_bytes(m, n, nb, fused=True, tail=True):
     """Algorithmic HBM bytes of the panel bidiagonalization (DESIGN.md 3.1 'bytes per unit').
     Per step: the fused pass reads the trailing block (m-i) x (n-i-1) once; the split passes read
     it twice ((m-i)(n-i-1) for the column dots, (m-i-1)(n-i-1) for the row dots); plus one read+write
     of the trailing block per panel for the deferred rank-2nb update.  The fused pass is used while
-    the trailing block has >= 128 rows and >= 32 columns (bidiag.cu:plan_fused).  Also returns the
+    the trailing block has >= 16 rows and >= 8 columns (bidiag.cu:plan_fused).  Also returns the
     survey's figure 12*S for the unblocked 3-transfer scheme."""
     mn = min(m, n)
     i = np.arange(mn - 1, dtype=np.float64)
     t1 = (m - i) * (n - i - 1)
     t2 = np.where(i < n - 2, (m - i - 1) * (n - i - 1), 0.0)
-    is_fused = (m - i >= 128) & (n - i - 1 >= 32) & (i < n - 2) if fused else np.zeros_like(i, dtype=bool)
-    reads = np.where(is_fused, t1, t1 + t2).sum()
-    ends = np.arange(nb - 1, mn - 1, nb, dtype=np.float64)
+    is_fused = (m - i >= 16) & (n - i - 1 >= 8) & (i < n - 2) if fused else np.zeros_like(i, dtype=bool)
+    per_step = np.where(is_fused, t1, t1 + t2)
+    # on-chip tail (bidiag_tail.cuh): from the first panel boundary where the trailing block fits the
+    # SMs' shared memory, the rest is ONE read of that block (bidiag.cu:tail_fits)
+    i_tail = mn
+    if tail and m >= n:
+        for i0 in range(0, mn, nb):
+            L0, R0 = m - i0, n - i0
+            if L0 <= 2048 and -(-R0 // 148) <= 16 and -(-R0 // 148) * ((L0 + 1) // 2 * 2) <= 28000:
+                i_tail = i0
+                break
+    reads = per_step[:i_tail].sum() + (float(m - i_tail) * (n - i_tail) if i_tail < mn else 0.0)
+    ends = np.arange(nb - 1, min(mn - 1, i_tail), nb, dtype=np.float64)
     upd = ((m - ends - 1) * (n - ends - 1)).sum()
     return 8.0 * reads + 16.0 * upd, 12.0 * (t1 + t2).sum()
 
@@ -298,7 +308,8 @@ def run_own(args):
         phase = {"bidiag_ms": ph[1], "ddc_ms": ph[2], "twisted_ms": ph[3], "backtransform_ms": ph[4]}
         pk, which = peaks()
         fused_on = os.environ.get("SVD_GPU_FUSED", "1") != "0"
-        b_alg, b_survey = bidiag_bytes(m, n, nb, fused_on)
+        tail_on = os.environ.get("SVD_GPU_TAIL", "1") != "0"
+        b_alg, b_survey = bidiag_bytes(m, n, nb, fused_on, tail_on)
         ach = b_alg / (ph[1] * 1e-3) / 1e9
         # single full-size passes of the two streaming kernels, timed alone
         wbytes = L.svdgpu_bidiag_workspace(m, n, m)
@@ -328,7 +339,8 @@ def run_own(args):
         ach_survey = b_survey / t_bd / 1e9          # SURVEY.md 8(d) definition: B_alg = 8 * 1.5 * S
         ach_own = b_alg / t_bd / 1e9                # bytes our scheme actually has to move
         roof = {"bound": "hbm",
-                "kernel": ("fused_pass_kernel (single-read pass; gemvT/gemvN below 128 rows) + finish_xf + panel GEMM"
+                "kernel": ("fused_pass_kernel (single-read pass) + finish_xf + panel GEMM (dgemm_ws_kernel); bidiag_tail_kernel "
+                           "once the trailing block fits on chip"
                            if fused_on else "gemvT_kernel + gemvN_kernel + finish_y/x + panel GEMM"),
                 "achieved": ach_survey, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach_survey / pk["hbm_gbs"],
                 "frac_of_8000_nominal": ach_survey / 8000.0,
@@ -337,7 +349,7 @@ def run_own(args):
                               "time from CUDA events (all bidiag launches); can exceed 1.0 because the panel-deferred "
                               "fused scheme moves fewer bytes than B_alg assumes - see own_scheme_*",
                 "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs, copy); bench/calib.cu read stream: 7200 GB/s",
-                "algorithmic_bytes": b_survey, "phase_ms": ph[1], "fused_pass": fused_on,
+                "algorithmic_bytes": b_survey, "phase_ms": ph[1], "fused_pass": fused_on, "on_chip_tail": tail_on,
                 "own_scheme_bytes": b_alg, "own_scheme_achieved": ach_own, "own_scheme_frac": ach_own / pk["hbm_gbs"],
                 **probe,
                 "backtransform_tflops": backxf_flops(m, n) / (ph[4] * 1e-3) / 1e12,

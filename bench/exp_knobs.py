@@ -24,7 +24,7 @@ st = torch.cuda.current_stream().cuda_stream
 torch.manual_seed(1)
 A = torch.rand((n, m), dtype=torch.float64, device=dev) * 3 + 1       # column-major m x n, ld m
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-KNOB_ENVS = ["SVD_GPU_NB_BIG", "SVD_GPU_NB_BIG_MIN", "SVD_GPU_GEMM_TILE", "SVD_GPU_GEMM_WS"]
+KNOB_ENVS = ["SVD_GPU_NB_BIG", "SVD_GPU_NB_BIG_MIN", "SVD_GPU_GEMM_TILE", "SVD_GPU_GEMM_WS", "SVD_GPU_TAIL"]
 
 
 def padded(rows, ld):
@@ -48,6 +48,7 @@ def run(cfg):
             w, mn_ = v.split(":"); os.environ["SVD_GPU_NB_BIG"] = w; os.environ["SVD_GPU_NB_BIG_MIN"] = mn_
         elif k == "tile": os.environ["SVD_GPU_GEMM_TILE"] = v
         elif k == "ws": os.environ["SVD_GPU_GEMM_WS"] = v
+        elif k == "tail": os.environ["SVD_GPU_TAIL"] = v
         else: raise SystemExit("unknown knob " + tok)
     L.svd_gpu_set_option(b"nb", nb)
     ld = m + pad

@@ -27,6 +27,8 @@
 namespace svdgpu {
 
 constexpr int NBMAX = 64;
+constexpr size_t TAIL_WS_SLOTS = (size_t)148 * 2048 + 3 * 2048 + 2 * 148 + 8;   // == TL_WS_SLOTS (bidiag_tail.cuh)
+constexpr int TAIL_DEFAULT_ON = 1;          // on-chip tail kernel (bidiag_tail.cuh)
 constexpr int NB_BIG_DEFAULT = 0;          // > 0: panel width while the trailing block is large (see bidiag_device)
 constexpr int NB_BIG_MIN_DEFAULT = 6144;   // trailing rows/columns from which NB_BIG is used
 constexpr int GT_CW = 4;          // columns per warp in gemvT
@@ -613,7 +615,9 @@ __global__ void col_init_kernel(const double *__restrict__ A, int m, long lda, d
 
 } // namespace svdgpu
 #include "bidiag_fused.cuh"
+#include "bidiag_tail.cuh"
 namespace svdgpu {
+static_assert(TAIL_WS_SLOTS == TL_WS_SLOTS, "workspace sizing of the on-chip tail");
 
 // ---------------------------------------------------------------------------------------
 constexpr int TMPN_ROWS = (BIDIAG_MAX_SPLIT > FZ_MAX_CLUSTERS) ? BIDIAG_MAX_SPLIT : FZ_MAX_CLUSTERS;
@@ -633,12 +637,14 @@ size_t bidiag_workspace_bytes(int m, int n, long lda)
     d += (size_t)(ceil_div(m, 128) + 130) * DOT_SLOTS; // dots1 partials (finish_xf row blocks)
     d += (size_t)FZ_MAX_CLUSTERS * DOT_SLOTS;          // dots2 partials (fused pass clusters)
     d += 8;                                // counters
+    d += 2 * TAIL_WS_SLOTS + 2;            // tagged exchange slots of the on-chip tail (16 bytes each, 16-byte aligned)
     return d * sizeof(double);
 }
 
 struct BidiagBufs {
     double *P, *Q, *c, *rv, *tmpT, *tmpN, *dots1, *dots2, *dots1p, *dots2p;
     unsigned *counters;
+    void *tail;
     long ldp, ldq;
 };
 static BidiagBufs carve(void *workspace, int m, int n, long lda)
@@ -656,7 +662,8 @@ static BidiagBufs carve(void *workspace, int m, int n, long lda)
     b.dots2 = w;  w += DOT_SLOTS;
     b.dots1p = w; w += (size_t)(ceil_div(m, 128) + 130) * DOT_SLOTS;
     b.dots2p = w; w += (size_t)FZ_MAX_CLUSTERS * DOT_SLOTS;
-    b.counters = (unsigned *)w;
+    b.counters = (unsigned *)w;             w += 8;
+    b.tail = (void *)(((uintptr_t)w + 15) & ~(uintptr_t)15);
     return b;
 }
 
@@ -826,6 +833,63 @@ static void fused_set_attributes()
     if (fc) force_cs = atoi(fc);
 }
 
+// ---- on-chip tail (bidiag_tail.cuh): from step i on, if the trailing block fits the SMs' shared memory
+static int g_tail_ctas = -1;            // co-resident CTAs of the tail kernel (0: not available)
+static bool tail_fits(int m, int n, int i)
+{
+    if (m < n || g_tail_ctas <= 0) return false;
+    const int L0 = m - i, R0 = n - i;
+    if (L0 > TL_MAXROWS || R0 < 1) return false;
+    const long Lp = round_up(L0, 2);
+    const int cpc = ceil_div(R0, g_tail_ctas);
+    return cpc <= TL_CPC && (long)cpc * Lp <= TL_CAP;
+}
+static void tail_init()
+{
+    if (g_tail_ctas >= 0) return;
+    g_tail_ctas = 0;
+    int dev = 0, nsm = 0, coop = 0, per_sm = 0;
+    SVD_CUDA_CHECK(cudaGetDevice(&dev));
+    SVD_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    SVD_CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    const int smem = (TL_CAP + TL_AUX) * (int)sizeof(double);
+    if (!coop) return;
+    if (cudaFuncSetAttribute(bidiag_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return;
+    }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bidiag_tail_kernel, TL_THREADS, smem) != cudaSuccess ||
+        per_sm < 1) {
+        (void)cudaGetLastError();
+        return;
+    }
+    g_tail_ctas = nsm < TL_MAXG ? nsm : TL_MAXG;
+}
+static void launch_tail(int m, int n, int i, double *A, long lda, double *alpha, double *beta, const BidiagBufs &b,
+                        cudaStream_t st)
+{
+    TailArgs ta;
+    ta.A = A; ta.lda = lda; ta.m = m; ta.n = n; ta.i0 = i; ta.alpha = alpha; ta.beta = beta;
+    TlSlot *sl = reinterpret_cast<TlSlot *>(b.tail);
+    ta.W = sl;   sl += (size_t)TL_MAXG * TL_MAXROWS;
+    ta.X = sl;   sl += TL_MAXROWS;
+    ta.C = sl;   sl += TL_MAXROWS;
+    ta.A1 = sl;  sl += TL_MAXROWS;
+    ta.RR = sl;  sl += 2 * TL_MAXG;
+    ta.R1 = sl;
+    ta.counter = b.counters + 8;
+    // tags start at 1: a zeroed slot is never valid
+    SVD_CUDA_CHECK(cudaMemsetAsync(b.tail, 0, TL_WS_SLOTS * sizeof(TlSlot), st));
+    ta.Lp = (int)round_up(m - i, 2);
+    const int cpc = ceil_div(n - i, g_tail_ctas);
+    const size_t smem = ((size_t)cpc * ta.Lp + TL_AUX) * sizeof(double);
+    SVD_CUDA_CHECK(cudaMemsetAsync(ta.counter, 0, sizeof(unsigned), st));
+    void *args[] = {&ta};
+    SVD_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)bidiag_tail_kernel, dim3(g_tail_ctas), dim3(TL_THREADS),
+                                               args, smem, st));
+    SVD_KERNEL_CHECK();
+}
+
 void bidiag_device(int m, int n, double *A, long lda, double *alpha, double *beta, void *workspace,
                    int nb, cudaStream_t st)
 {
@@ -848,6 +912,10 @@ void bidiag_device(int m, int n, double *A, long lda, double *alpha, double *bet
     // thresholds below which the split passes are used (overridable for tests)
     const char *e1 = getenv("SVD_GPU_FUSED_MIN_ROWS"), *e2 = getenv("SVD_GPU_FUSED_MIN_COLS");
     const int fz_min_rows = e1 ? atoi(e1) : FZ_MIN_ROWS, fz_min_cols = e2 ? atoi(e2) : FZ_MIN_COLS;
+    // SVD_GPU_TAIL=0/1: finish on chip once the trailing block fits into shared memory (bidiag_tail.cuh)
+    const char *tenv = getenv("SVD_GPU_TAIL");
+    const bool use_tail = tenv ? (tenv[0] != '0') : (TAIL_DEFAULT_ON != 0);
+    if (use_tail) tail_init();
     bool dots1_ready = false;       // dots1p holds dots1_parts partial dot vectors of the current column c
     int dots1_parts = 0;
     // Panel width schedule.  The deferred trailing update is a K = 2nb GEMM that reads and writes the
@@ -873,6 +941,11 @@ void bidiag_device(int m, int n, double *A, long lda, double *alpha, double *bet
     int k = 0;
     for (int i = 0; i < mn; ++i) {              // steps 0..mn-2 regular, step mn-1 is the tail
         const bool tail = (i == mn - 1);
+        if (use_tail && k == 0 && tail_fits(m, n, i)) {
+            // the rest of the factorization in one cooperative launch with the matrix on chip
+            launch_tail(m, n, i, A, lda, alpha, beta, b, st);
+            break;
+        }
         if (k == 0) {
             const int nb_next = (m - i >= nb_big_min && n - i >= nb_big_min) ? nb_big : nb_small;
             // the dot slots finish_xf left for this step are laid out for the previous panel's width

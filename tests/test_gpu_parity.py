@@ -67,6 +67,35 @@ def test_bidiag_vs_golden_reference(D, name):
     assert np.abs(ag - g["alpha"]).max() <= 1e-9 and np.abs(bg - g["beta"]).max() <= 1e-9
 
 
+@pytest.mark.parametrize("shape", [(1, 1), (2, 2), (3, 3), (5, 4), (33, 33), (64, 64), (200, 200), (513, 512),
+                                   (300, 200), (97, 3), (40, 1), (1500, 1400), (2040, 1100), (2100, 2000),
+                                   (2500, 2500)])
+def test_bidiag_on_chip_tail(D, shape, monkeypatch):
+    # bidiag_tail.cuh: once the trailing block fits the SMs' shared memory the rest of the factorization runs
+    # in one cooperative launch (small inputs entirely, larger ones from the first panel boundary that fits)
+    monkeypatch.setenv("SVD_GPU_TAIL", "1")
+    m, n = shape
+    A = util.rand_matrix(m, n, 1.0, 2.0, 4)
+    Ao, ao, bo = util.oracle_bidiag(A)
+    Ag, ag, bg = D.bidiag_par(A)
+    assert not np.isnan(Ag).any()
+    assert np.abs(Ag - Ao).max() <= 1e-9
+    assert np.abs(ag - ao).max() <= 1e-9
+    if bo.size:
+        assert np.abs(bg - bo).max() <= 1e-9
+    monkeypatch.setenv("SVD_GPU_TAIL", "0")
+    A0, a0, b0 = D.bidiag_par(A)
+    assert np.abs(Ag - A0).max() <= 1e-9 and np.abs(ag - a0).max() <= 1e-9
+
+
+def test_svd_gpu_with_on_chip_tail(D, monkeypatch):
+    monkeypatch.setenv("SVD_GPU_TAIL", "1")
+    for shape in [(700, 700), (2304, 2304), (3000, 1200)]:
+        A = util.rand_matrix(*shape)
+        sigma, U, V, _ = D.svd_gpu(A)
+        check_lapack_bounds(A, sigma, U, V)
+
+
 @pytest.mark.parametrize("nb", [1, 7, 32, 64])
 def test_bidiag_panel_width_invariance(D, nb):
     # the deferred-update panel width is an implementation detail: results must not depend on it
