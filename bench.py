@@ -64,12 +64,9 @@ def bidiag_bytes(m, n, nb, fused=True, tail=True):
     # on-chip tail (bidiag_tail.cuh): from the first panel boundary where the trailing block fits the
     # SMs' shared memory, the rest is ONE read of that block (bidiag.cu:tail_fits)
     i_tail = mn
-    if tail and m >= n:
-        for i0 in range(0, mn, nb):
-            L0, R0 = m - i0, n - i0
-            if L0 <= 2048 and -(-R0 // 148) <= 16 and -(-R0 // 148) * ((L0 + 1) // 2 * 2) <= 28000:
-                i_tail = i0
-                break
+    if tail:
+        import ddc_svd_b200 as D
+        i_tail = D.lib().svdgpu_bidiag_tail_start(m, n, nb, 148)      # the library's own planning rule
     reads = per_step[:i_tail].sum() + (float(m - i_tail) * (n - i_tail) if i_tail < mn else 0.0)
     ends = np.arange(nb - 1, min(mn - 1, i_tail), nb, dtype=np.float64)
     upd = ((m - ends - 1) * (n - ends - 1)).sum()

@@ -90,6 +90,7 @@ SIGNATURES = [
     ("svdgpu_host_free", None, [c_void_p]),
     ("svdgpu_bidiag_workspace", c_size_t, [c_int, c_int, c_long]),
     ("svdgpu_bidiag", None, [c_int, c_int, c_void_p, c_long, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    ("svdgpu_bidiag_tail_start", c_int, [c_int, c_int, c_int, c_int]),
     ("svdgpu_ddc_workspace", c_size_t, [c_int]),
     ("svdgpu_ddc_values", None, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     ("svdgpu_twisted_workspace", c_size_t, [c_int, c_int, c_int]),

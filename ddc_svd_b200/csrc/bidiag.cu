@@ -835,14 +835,27 @@ static void fused_set_attributes()
 
 // ---- on-chip tail (bidiag_tail.cuh): from step i on, if the trailing block fits the SMs' shared memory
 static int g_tail_ctas = -1;            // co-resident CTAs of the tail kernel (0: not available)
-static bool tail_fits(int m, int n, int i)
+// does the trailing block of step i fit the shared memory of `ctas` CTAs (columns dealt round-robin)?
+static bool tail_fits_ctas(int m, int n, int i, int ctas)
 {
-    if (m < n || g_tail_ctas <= 0) return false;
+    if (m < n || ctas <= 0) return false;
     const int L0 = m - i, R0 = n - i;
     if (L0 > TL_MAXROWS || R0 < 1) return false;
     const long Lp = round_up(L0, 2);
-    const int cpc = ceil_div(R0, g_tail_ctas);
+    const int cpc = ceil_div(R0, ctas);
     return cpc <= TL_CPC && (long)cpc * Lp <= TL_CAP;
+}
+static bool tail_fits(int m, int n, int i) { return tail_fits_ctas(m, n, i, g_tail_ctas); }
+// First step handed to the on-chip tail kernel (a panel boundary: multiples of nb), min(m,n) if none.
+// Pure planning, no device needed (used by bench.py's byte accounting and by the CPU tests).
+int bidiag_tail_start(int m, int n, int nb, int ctas)
+{
+    const int mn = m < n ? m : n;
+    if (nb <= 0 || nb > NBMAX) nb = 32;
+    if (ctas > TL_MAXG) ctas = TL_MAXG;
+    for (int i = 0; i < mn; i += nb)
+        if (tail_fits_ctas(m, n, i, ctas)) return i;
+    return mn;
 }
 static void tail_init()
 {

@@ -13,5 +13,7 @@ void bidiag_device(int m, int n, double *A, long lda, double *alpha, double *bet
                    int nb, cudaStream_t st);
 // which = 0: one gemvT pass, 1: one gemvN pass over the full matrix (workspace as above; its
 // vector buffers must have been initialised, e.g. by a previous bidiag_device call or a memset)
+// first step of the on-chip tail (bidiag_tail.cuh) for `ctas` co-resident CTAs; min(m,n) when it never fits
+int bidiag_tail_start(int m, int n, int nb, int ctas);
 void bidiag_pass_probe(int m, int n, const double *A, long lda, void *workspace, int which, cudaStream_t st);
 }

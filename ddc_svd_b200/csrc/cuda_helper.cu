@@ -119,6 +119,7 @@ unsigned long long svdgpu_launch_count(void) { return g_svdgpu_launches; }
 
 // ---- kernel families -------------------------------------------------------------------
 size_t svdgpu_bidiag_workspace(int m, int n, long lda) { return bidiag_workspace_bytes(m, n, lda); }
+int svdgpu_bidiag_tail_start(int m, int n, int nb, int ctas) { return bidiag_tail_start(m, n, nb, ctas); }
 void svdgpu_bidiag(int m, int n, double *dA, long lda, double *dalpha, double *dbeta, void *dwork, int nb,
                    void *stream)
 {

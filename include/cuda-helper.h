@@ -52,6 +52,9 @@ void   svdgpu_host_free(void *p);
 size_t svdgpu_bidiag_workspace(int m, int n, long lda);
 void   svdgpu_bidiag(int m, int n, double *dA, long lda, double *dalpha, double *dbeta,
                      void *dwork, int nb, void *stream);
+/* planning only (no device): the first step that the on-chip tail kernel takes over when `ctas`
+ * CTAs are co-resident (148 on a B200), min(m,n) if the trailing block never fits */
+int    svdgpu_bidiag_tail_start(int m, int n, int nb, int ctas);
 /* dDC singular values (Calculations-Parallel.c:852-874); b1,b2 of length N; synchronises. */
 size_t svdgpu_ddc_workspace(int N);
 void   svdgpu_ddc_values(int N, const double *db1, const double *db2, double *dsigma,

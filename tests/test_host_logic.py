@@ -110,3 +110,22 @@ def test_device_numerics_model_meets_bounds(n):
     assert np.linalg.norm(X @ X.T - np.eye(n)) < c
     assert np.linalg.norm(Y @ Y.T - np.eye(n)) < c
     assert np.linalg.norm(B - Y.T @ np.diag(sig2) @ X) / np.linalg.norm(B) < c
+
+
+def test_on_chip_tail_planning():
+    # bidiag.cu:bidiag_tail_start - pure host logic: the tail kernel takes over at the first panel boundary
+    # whose trailing block fits 148 x 28000 doubles of shared memory (<= 2048 rows, <= 16 columns per CTA)
+    import ddc_svd_b200 as D
+    f = D.lib().svdgpu_bidiag_tail_start
+    assert f(512, 512, 32, 148) == 0 and f(1, 1, 32, 148) == 0          # small inputs: entirely on chip
+    assert f(1500, 1400, 32, 148) == 0
+    i0 = f(4096, 4096, 32, 148)
+    assert i0 % 32 == 0 and 0 < i0 < 4096
+    L = 4096 - i0
+    assert L <= 2048 and -(-L // 148) * L <= 28000                      # fits ...
+    Lprev = L + 32
+    assert Lprev > 2048 or -(-Lprev // 148) * Lprev > 28000             # ... and the boundary before did not
+    assert f(16384, 16384, 32, 148) == 16384 - L                        # same trailing size for any square input
+    assert f(200, 300, 32, 148) == 200                                  # wide inputs never (they arrive transposed)
+    assert f(65536, 4096, 32, 148) == 4096                              # too tall: 61k rows never fit
+    assert f(4096, 4096, 32, 8) == 4096 - 128                           # fewer CTAs: 8 x 16 columns at most
