@@ -74,6 +74,7 @@ void dgemm_dmma(const GemmArgs &g, cudaStream_t st);
 // persistent warp-specialised variant (dgemm_ws.cu); dgemm_dmma() routes eligible shapes to it
 constexpr int DGEMM_WS_DEFAULT = 1;
 bool dgemm_ws_enabled();
+int dgemm_ws_mode();
 bool dgemm_ws_eligible(const GemmArgs &g);
 void dgemm_ws(const GemmArgs &g, cudaStream_t st);
 void transpose_device(int m, int n, const double *A, long lda, double *At, long ldat, cudaStream_t st);

@@ -218,11 +218,12 @@ template <bool TA, bool TB> static void launch_t(const GemmArgs &g, cudaStream_t
 
 // SVD_GPU_GEMM_WS=0/1 overrides the default choice between the one-tile-per-CTA kernel of this file
 // and the persistent warp-specialised kernel of dgemm_ws.cu (read on every call: tests flip it)
-bool dgemm_ws_enabled()
+int dgemm_ws_mode()
 {
     const char *e = getenv("SVD_GPU_GEMM_WS");
-    return e ? (e[0] != '0') : (DGEMM_WS_DEFAULT != 0);
+    return e ? atoi(e) : DGEMM_WS_DEFAULT;      // 0: off, 1: 128 x 64 tiles, one CTA per SM, 2: 64 x 64 tiles, two per SM
 }
+bool dgemm_ws_enabled() { return dgemm_ws_mode() != 0; }
 
 void dgemm_dmma(const GemmArgs &gin, cudaStream_t st)
 {

@@ -23,22 +23,26 @@ namespace svdgpu {
 
 namespace {
 
-constexpr int WS_BM = 128, WS_BN = 64, WS_BK = 16;
-constexpr int WS_CONS_WARPS = 8, WS_PROD_WARPS = 4;
-constexpr int WS_CONS = WS_CONS_WARPS * 32, WS_PROD = WS_PROD_WARPS * 32;
-constexpr int WS_THREADS = WS_CONS + WS_PROD;
-constexpr int WS_LDC_S = WS_BM + 2;       // 2*tq*130 + gq: the accumulator loads of a half-warp hit 16 distinct banks
+constexpr int WS_BN = 64, WS_BK = 16;
+// BM = 128: one 384-thread CTA per SM (8 consumer + 4 producer warps), the default.
+// BM = 64 (SVD_GPU_GEMM_WS=2, experiment): two 192-thread CTAs per SM (4 + 2 warps) on 64 x 64 tiles, so that
+// one CTA's C-tile load / epilogue overlaps the other's DMMAs (short-K updates), at 33 % more operand traffic.
 
 // HASC: the accumulators start from a staged C tile (updates): 4 stages + the C buffer.  Pure products
 // (W = V^T C streams its B operand from HBM) get 6 stages and no C buffer instead.
-template <bool TA, bool TB, bool HASC> struct WsCfg {
-    static constexpr int STAGES = HASC ? 4 : 6;
-    static constexpr int LDA_S = TA ? (WS_BK + 4) : (WS_BM + 4);
+template <int BM, bool TA, bool TB, bool HASC> struct WsCfg {
+    static constexpr int CONS_WARPS = (BM / 32) * (WS_BN / 32), PROD_WARPS = BM / 32;
+    static constexpr int CONS = CONS_WARPS * 32, PROD = PROD_WARPS * 32;      // PROD == BM: one tile row per producer thread
+    static constexpr int THREADS = CONS + PROD;
+    static constexpr int CTAS_PER_SM = (BM == 64) ? 2 : 1;
+    static constexpr int STAGES = HASC ? (BM == 64 ? 3 : 4) : (BM == 64 ? 4 : 6);
+    static constexpr int LDC_S = BM + 2;      // 2*tq*(BM+2) + gq: the accumulator loads of a half-warp hit 16 distinct banks
+    static constexpr int LDA_S = TA ? (WS_BK + 4) : (BM + 4);
     static constexpr int LDB_S = TB ? (WS_BN + 4) : (WS_BK + 4);
-    static constexpr int A_ELEMS = TA ? WS_BM * LDA_S : WS_BK * LDA_S;
+    static constexpr int A_ELEMS = TA ? BM * LDA_S : WS_BK * LDA_S;
     static constexpr int B_ELEMS = TB ? WS_BK * LDB_S : WS_BN * LDB_S;
     static constexpr int STAGE_ELEMS = A_ELEMS + B_ELEMS;
-    static constexpr int C_ELEMS = HASC ? WS_BN * WS_LDC_S : 0;
+    static constexpr int C_ELEMS = HASC ? WS_BN * LDC_S : 0;
     static constexpr int NBAR = 2 * STAGES + 2;
     static constexpr size_t SMEM_BYTES = (size_t)(STAGES * STAGE_ELEMS + C_ELEMS) * 8 + NBAR * 8 + 16;
 };
@@ -118,13 +122,14 @@ __device__ __forceinline__ double ws_neg(double x)
 struct WsUnit { int m0, n0, kbeg, kend, zs; };
 
 // unit u -> tile (m fastest, so that neighbouring CTAs share the B tile in L2) and K slice
+template <int BM>
 __device__ __forceinline__ WsUnit ws_unit(const GemmArgs &g, int u, int tilesM, int ntiles)
 {
     WsUnit w;
     w.zs = u / ntiles;
     const int t = u - w.zs * ntiles;
     const int tn = t / tilesM;
-    w.m0 = (t - tn * tilesM) * WS_BM;
+    w.m0 = (t - tn * tilesM) * BM;
     w.n0 = tn * WS_BN;
     w.kbeg = 0; w.kend = g.K;
     if (g.splitk > 1) {
@@ -135,12 +140,15 @@ __device__ __forceinline__ WsUnit ws_unit(const GemmArgs &g, int u, int tilesM, 
     return w;
 }
 
-template <bool TA, bool TB, bool HASC>
-__global__ void __launch_bounds__(WS_THREADS, 1)
+template <int BM, bool TA, bool TB, bool HASC>
+__global__ void __launch_bounds__(WsCfg<BM, TA, TB, HASC>::THREADS, WsCfg<BM, TA, TB, HASC>::CTAS_PER_SM)
 dgemm_ws_kernel(GemmArgs g, int tilesM, int ntiles, int nunits)
 {
-    using Cfg = WsCfg<TA, TB, HASC>;
+    using Cfg = WsCfg<BM, TA, TB, HASC>;
     constexpr int WS_STAGES = Cfg::STAGES;
+    constexpr int WS_CONS = Cfg::CONS, WS_PROD = Cfg::PROD, WS_CONS_WARPS = Cfg::CONS_WARPS, WS_LDC_S = Cfg::LDC_S;
+    constexpr int WS_BM = BM;
+    constexpr int PG = WS_PROD / 16;          // tile rows (k-contiguous operands) a producer pass covers
     extern __shared__ __align__(16) double smem[];
     double *Cs = smem + WS_STAGES * Cfg::STAGE_ELEMS;
     uint64_t *bars = reinterpret_cast<uint64_t *>(Cs + Cfg::C_ELEMS);
@@ -172,7 +180,7 @@ dgemm_ws_kernel(GemmArgs g, int tilesM, int ntiles, int nunits)
         };
         unsigned it = 0, tl = 0;
         for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++tl) {
-            const WsUnit w = ws_unit(g, u, tilesM, ntiles);
+            const WsUnit w = ws_unit<BM>(g, u, tilesM, ntiles);
             const int nk = (w.kend > w.kbeg) ? (w.kend - w.kbeg + WS_BK - 1) / WS_BK : 0;
             if (has_c && tl == 0) { load_c(w); ws_cp_async_arrive(cfull); }
             const int cpoint = (nk < WS_STAGES ? nk : WS_STAGES) - 1;      // after this k-step: stage the next C tile
@@ -194,8 +202,8 @@ dgemm_ws_kernel(GemmArgs g, int tilesM, int ntiles, int nunits)
                     const int kk = p & 15, mb = p >> 4;
                     const bool kok = (k0 + kk < w.kend);
 #pragma unroll
-                    for (int j = 0; j < WS_BM / 8; ++j) {
-                        const int mm = mb + 8 * j;
+                    for (int j = 0; j < WS_BM / PG; ++j) {
+                        const int mm = mb + PG * j;
                         const bool ok = kok && (w.m0 + mm < g.M);
                         ws_cp_async8(As + mm * Cfg::LDA_S + kk, ok ? g.A + (k0 + kk) + (long)(w.m0 + mm) * g.lda : g.A, ok);
                     }
@@ -204,17 +212,18 @@ dgemm_ws_kernel(GemmArgs g, int tilesM, int ntiles, int nunits)
                     const int kk = p & 15, nb0 = p >> 4;
                     const bool kok = (k0 + kk < w.kend);
 #pragma unroll
-                    for (int j = 0; j < WS_BN / 8; ++j) {
-                        const int nn = nb0 + 8 * j;
+                    for (int j = 0; j < WS_BN / PG; ++j) {
+                        const int nn = nb0 + PG * j;
                         const bool ok = kok && (w.n0 + nn < g.N);
                         ws_cp_async8(Bs + nn * Cfg::LDB_S + kk, ok ? g.B + (k0 + kk) + (long)(w.n0 + nn) * g.ldb : g.B, ok);
                     }
                 } else {            // B stored N x K, n contiguous -> Bs[k][n]
+                    constexpr int KG = WS_PROD / WS_BN;           // k rows per producer pass (2 or 1)
                     const int nn = p & 63, kb = p >> 6;
                     const bool nok = (w.n0 + nn < g.N);
 #pragma unroll
-                    for (int j = 0; j < WS_BK / 2; ++j) {
-                        const int kk = kb + 2 * j;
+                    for (int j = 0; j < WS_BK / KG; ++j) {
+                        const int kk = kb + KG * j;
                         const bool ok = nok && (k0 + kk < w.kend);
                         ws_cp_async8(Bs + kk * Cfg::LDB_S + nn, ok ? g.B + (w.n0 + nn) + (long)(k0 + kk) * g.ldb : g.B, ok);
                     }
@@ -225,7 +234,7 @@ dgemm_ws_kernel(GemmArgs g, int tilesM, int ntiles, int nunits)
                     if (un < nunits) {
                         // the consumers hand the C buffer back as soon as this unit's accumulators are loaded
                         ws_mbar_wait(cempty, (tl & 1u));
-                        load_c(ws_unit(g, un, tilesM, ntiles));
+                        load_c(ws_unit<BM>(g, un, tilesM, ntiles));
                         ws_cp_async_arrive(cfull);
                     }
                 }
@@ -234,7 +243,7 @@ dgemm_ws_kernel(GemmArgs g, int tilesM, int ntiles, int nunits)
                 const int un = u + gridDim.x;
                 if (un < nunits) {
                     ws_mbar_wait(cempty, (tl & 1u));
-                    load_c(ws_unit(g, un, tilesM, ntiles));
+                    load_c(ws_unit<BM>(g, un, tilesM, ntiles));
                     ws_cp_async_arrive(cfull);
                 }
             }
@@ -246,7 +255,7 @@ dgemm_ws_kernel(GemmArgs g, int tilesM, int ntiles, int nunits)
     // ---------------------------------------------------------------------- consumers
     const int lane = tid & 31, warp = tid >> 5;
     const int gq = lane >> 2, tq = lane & 3;
-    const int wm0 = (warp & 3) * 32, wn0 = (warp >> 2) * 32;
+    const int wm0 = (warp % (WS_BM / 32)) * 32, wn0 = (warp / (WS_BM / 32)) * 32;
     const double sc = has_c ? g.beta * g.alpha : 0.0;      // beta/alpha for alpha = +-1
     // +-1 scalings are sign flips on the integer pipe: the FP64 pipe belongs to the DMMAs
     const int smode = (sc == 1.0) ? 1 : (sc == -1.0 ? 2 : 0);
@@ -267,7 +276,7 @@ dgemm_ws_kernel(GemmArgs g, int tilesM, int ntiles, int nunits)
     };
     unsigned it = 0, tl = 0;
     for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++tl) {
-        const WsUnit w = ws_unit(g, u, tilesM, ntiles);
+        const WsUnit w = ws_unit<BM>(g, u, tilesM, ntiles);
         const int nk = (w.kend > w.kbeg) ? (w.kend - w.kbeg + WS_BK - 1) / WS_BK : 0;
         double acc[4][4][2];
         if (has_c) {
@@ -369,27 +378,32 @@ dgemm_ws_kernel(GemmArgs g, int tilesM, int ntiles, int nunits)
     }
 }
 
-template <bool TA, bool TB, bool HASC> void launch_ws_c(const GemmArgs &g, cudaStream_t st)
+template <int BM, bool TA, bool TB, bool HASC> void launch_ws_c(const GemmArgs &g, cudaStream_t st)
 {
-    using Cfg = WsCfg<TA, TB, HASC>;
+    using Cfg = WsCfg<BM, TA, TB, HASC>;
     static int nsm = 0;
     int dev = 0;
     SVD_CUDA_CHECK(cudaGetDevice(&dev));
     if (nsm == 0) SVD_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
     // per-device attribute; cheap enough to set on every launch (multi-GPU safe)
-    SVD_CUDA_CHECK(cudaFuncSetAttribute(dgemm_ws_kernel<TA, TB, HASC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SVD_CUDA_CHECK(cudaFuncSetAttribute(dgemm_ws_kernel<BM, TA, TB, HASC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)Cfg::SMEM_BYTES));
-    const int tilesM = ceil_div(g.M, WS_BM), tilesN = ceil_div(g.N, WS_BN);
+    const int tilesM = ceil_div(g.M, BM), tilesN = ceil_div(g.N, WS_BN);
     const int ntiles = tilesM * tilesN, nunits = ntiles * g.splitk;
-    const int grid = nunits < nsm ? nunits : nsm;
-    dgemm_ws_kernel<TA, TB, HASC><<<grid, WS_THREADS, Cfg::SMEM_BYTES, st>>>(g, tilesM, ntiles, nunits);
+    const int slots = nsm * Cfg::CTAS_PER_SM;
+    const int grid = nunits < slots ? nunits : slots;
+    dgemm_ws_kernel<BM, TA, TB, HASC><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(g, tilesM, ntiles, nunits);
     SVD_KERNEL_CHECK();
 }
 
 template <bool TA, bool TB> void launch_ws(const GemmArgs &g, cudaStream_t st)
 {
-    if (g.splitk <= 1 && g.beta != 0.0) launch_ws_c<TA, TB, true>(g, st);
-    else launch_ws_c<TA, TB, false>(g, st);
+    const bool hasc = (g.splitk <= 1 && g.beta != 0.0);
+    if (dgemm_ws_mode() == 2) {
+        if (hasc) launch_ws_c<64, TA, TB, true>(g, st); else launch_ws_c<64, TA, TB, false>(g, st);
+    } else {
+        if (hasc) launch_ws_c<128, TA, TB, true>(g, st); else launch_ws_c<128, TA, TB, false>(g, st);
+    }
 }
 
 } // namespace

@@ -377,7 +377,8 @@ def test_svd_gpu_vs_oracle_512(D):
                                   (0, 1, 1000, 900, 64), (0, 0, 700, 513, 128), (0, 1, 256, 256, 16),
                                   (0, 0, 1531, 777, 100), (0, 1, 4100, 300, 64)])
 @pytest.mark.parametrize("alpha_beta", [(-1.0, 1.0), (1.0, 1.0), (0.5, 0.0), (0.5, 2.0)])
-@pytest.mark.parametrize("ws", ["0", "1"])
+# ws = 2 (64 x 64 tiles, two CTAs per SM) is an experiment that is not the default: SVD_TEST_EXPERIMENTAL=1 adds it
+@pytest.mark.parametrize("ws", ["0", "1"] + (["2"] if os.environ.get("SVD_TEST_EXPERIMENTAL") else []))
 def test_dgemm_vs_numpy(D, case, alpha_beta, ws, monkeypatch):
     # (transA, transB, M, N, K).  ws = 1: updates (alpha = +-1, beta != 0) and pure products with M > 64
     # go to the persistent warp-specialised kernel (dgemm_ws.cu), everything else - and everything
