@@ -835,6 +835,8 @@ static void fused_set_attributes()
 
 // ---- on-chip tail (bidiag_tail.cuh): from step i on, if the trailing block fits the SMs' shared memory
 static int g_tail_ctas = -1;            // co-resident CTAs of the tail kernel (0: not available)
+static bool g_tail2_ok = false;
+static int g_tail_mode = 1;             // SVD_GPU_TAIL: 1 = kernel version 1 (default), 2 = experimental version 2
 // does the trailing block of step i fit the shared memory of `ctas` CTAs (columns dealt round-robin)?
 static bool tail_fits_ctas(int m, int n, int i, int ctas)
 {
@@ -867,11 +869,17 @@ static void tail_init()
     SVD_CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
     const int smem = (TL_CAP + TL_AUX) * (int)sizeof(double);
     if (!coop) return;
-    if (cudaFuncSetAttribute(bidiag_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+    // the experimental version 2 must not be able to disable the default one
+    int per_sm2 = 0;
+    g_tail2_ok = cudaFuncSetAttribute(bidiag_tail_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess &&
+                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, bidiag_tail_kernel<2>, TL_THREADS, smem) == cudaSuccess &&
+                 per_sm2 >= 1;
+    (void)cudaGetLastError();
+    if (cudaFuncSetAttribute(bidiag_tail_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
         (void)cudaGetLastError();
         return;
     }
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bidiag_tail_kernel, TL_THREADS, smem) != cudaSuccess ||
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bidiag_tail_kernel<1>, TL_THREADS, smem) != cudaSuccess ||
         per_sm < 1) {
         (void)cudaGetLastError();
         return;
@@ -898,8 +906,8 @@ static void launch_tail(int m, int n, int i, double *A, long lda, double *alpha,
     const size_t smem = ((size_t)cpc * ta.Lp + TL_AUX) * sizeof(double);
     SVD_CUDA_CHECK(cudaMemsetAsync(ta.counter, 0, sizeof(unsigned), st));
     void *args[] = {&ta};
-    SVD_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)bidiag_tail_kernel, dim3(g_tail_ctas), dim3(TL_THREADS),
-                                               args, smem, st));
+    const void *fn = (g_tail_mode == 2 && g_tail2_ok) ? (const void *)bidiag_tail_kernel<2> : (const void *)bidiag_tail_kernel<1>;
+    SVD_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(g_tail_ctas), dim3(TL_THREADS), args, smem, st));
     SVD_KERNEL_CHECK();
 }
 
@@ -928,6 +936,7 @@ void bidiag_device(int m, int n, double *A, long lda, double *alpha, double *bet
     // SVD_GPU_TAIL=0/1: finish on chip once the trailing block fits into shared memory (bidiag_tail.cuh)
     const char *tenv = getenv("SVD_GPU_TAIL");
     const bool use_tail = tenv ? (tenv[0] != '0') : (TAIL_DEFAULT_ON != 0);
+    g_tail_mode = (tenv && tenv[0] == '2') ? 2 : 1;
     if (use_tail) tail_init();
     bool dots1_ready = false;       // dots1p holds dots1_parts partial dot vectors of the current column c
     int dots1_parts = 0;

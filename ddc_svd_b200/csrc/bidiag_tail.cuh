@@ -124,6 +124,27 @@ __device__ __forceinline__ double tl_poll_sum(const TlSlot *base, int G, unsigne
     return warp_sum(((sv[0] + sv[1]) + (sv[2] + sv[3])) + sv[4]);
 }
 
+// one reflector from (first entry, squared norm).  VER 2: one sqrt and one rsqrt on the critical path instead of
+// two square roots and a divide (same value up to rounding: inv = 1 / (sqrt(2) sqrt(nu^2 + |nu x0|)))
+template <int VER> __device__ __forceinline__ Refl tl_refl(double x0, double nrm2)
+{
+    if constexpr (VER == 1) {
+        return make_refl(x0, nrm2);
+    } else {
+        Refl f;
+        const double nu = sqrt(nrm2);
+        f.snu = (x0 < 0.0) ? -nu : nu;
+        const double q = nu * nu + fabs(nu * x0);
+        f.inv = (q > 0.0) ? rsqrt(2.0 * q) : 0.0;
+        return f;
+    }
+}
+
+// VER 1: the version validated and measured in round 1 (default).
+// VER 2 (SVD_GPU_TAIL=2, experiment): sweeps as loops over the live columns only (the 16 x 4 unrolled code of VER 1
+// is 2 900 instructions and misses the instruction cache), the cheaper reflector, and polls that re-read only the
+// slots that had not arrived (every retry of VER 1 re-reads all of x and c': 4.9 MB of L2 traffic per round at 1024 rows).
+template <int VER>
 __global__ void __launch_bounds__(TL_THREADS, 1) bidiag_tail_kernel(TailArgs p)
 {
     extern __shared__ __align__(16) double tl_sm[];
@@ -162,7 +183,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) bidiag_tail_kernel(TailArgs p)
     for (int i = i0; i < n; ++i) {
         const int lo = i - i0;                           // first active local row
         // ---- column reflector from (c, c.c): v = (c + s*nu*e_i) * inv, alpha_i = -s*nu
-        const Refl f = make_refl(ci, cc);
+        const Refl f = tl_refl<VER>(ci, cc);
         double v[TL_RPT];
 #pragma unroll
         for (int z = 0; z < TL_RPT; ++z) {
@@ -183,30 +204,49 @@ __global__ void __launch_bounds__(TL_THREADS, 1) bidiag_tail_kernel(TailArgs p)
         const int qlo_c = qlo < 0 ? 0 : qlo;
 
         // ---- sweep 1: pending right update of step i-1 (a -= x u_j), column dots t_j = v^T a_j
-        double pq[TL_CPC];
+        if constexpr (VER == 1) {
+            double pq[TL_CPC];
 #pragma unroll
-        for (int q = 0; q < TL_CPC; ++q) {
-            pq[q] = 0.0;
-            if (q >= qlo_c && q < ncol) {
+            for (int q = 0; q < TL_CPC; ++q) {
+                pq[q] = 0.0;
+                if (q >= qlo_c && q < ncol) {
+                    const double uq = s_u[q];
+                    double *col = a + q * Lp;
+#pragma unroll
+                    for (int z = 0; z < TL_RPT; ++z) {
+                        const int rho = t + z * TL_THREADS;
+                        if (rho >= lo && rho < L0) {
+                            const double aa = col[rho] - xr[z] * uq;
+                            col[rho] = aa;
+                            pq[q] += v[z] * aa;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < TL_CPC; ++q)
+                if (q >= qlo_c && q < ncol) {                // CTA-uniform
+                    const double s = warp_sum(pq[q]);
+                    if (lane == 0) s_red[warp * (TL_CPC + 1) + q] = s;
+                }
+        } else {
+            for (int q = qlo_c; q < ncol; ++q) {
                 const double uq = s_u[q];
                 double *col = a + q * Lp;
+                double pp = 0.0;
 #pragma unroll
                 for (int z = 0; z < TL_RPT; ++z) {
                     const int rho = t + z * TL_THREADS;
                     if (rho >= lo && rho < L0) {
                         const double aa = col[rho] - xr[z] * uq;
                         col[rho] = aa;
-                        pq[q] += v[z] * aa;
+                        pp += v[z] * aa;
                     }
                 }
+                pp = warp_sum(pp);
+                if (lane == 0) s_red[warp * (TL_CPC + 1) + q] = pp;
             }
         }
-#pragma unroll
-        for (int q = 0; q < TL_CPC; ++q)
-            if (q >= qlo_c && q < ncol) {                // CTA-uniform
-                const double s = warp_sum(pq[q]);
-                if (lane == 0) s_red[warp * (TL_CPC + 1) + q] = s;
-            }
         __syncthreads();
         if (t < TL_CPC && t >= qlo_c && t < ncol) {
             double s = 0.0;
@@ -224,9 +264,26 @@ __global__ void __launch_bounds__(TL_THREADS, 1) bidiag_tail_kernel(TailArgs p)
 #pragma unroll
         for (int z = 0; z < TL_RPT; ++z) w[z] = 0.0;
         double rr = 0.0;
+        if constexpr (VER == 1) {
 #pragma unroll
-        for (int q = 0; q < TL_CPC; ++q) {
-            if (q >= qlo_c && q < ncol) {
+            for (int q = 0; q < TL_CPC; ++q) {
+                if (q >= qlo_c && q < ncol) {
+                    const double tq2 = 2.0 * s_t[q], rq = s_r[q];
+                    double *col = a + q * Lp;
+                    rr += rq * rq;
+#pragma unroll
+                    for (int z = 0; z < TL_RPT; ++z) {
+                        const int rho = t + z * TL_THREADS;
+                        if (rho > lo && rho < L0) {
+                            const double aa = col[rho] - v[z] * tq2;
+                            col[rho] = aa;
+                            w[z] += aa * rq;
+                        }
+                    }
+                }
+            }
+        } else {
+            for (int q = qlo_c; q < ncol; ++q) {
                 const double tq2 = 2.0 * s_t[q], rq = s_r[q];
                 double *col = a + q * Lp;
                 rr += rq * rq;
@@ -274,17 +331,38 @@ __global__ void __launch_bounds__(TL_THREADS, 1) bidiag_tail_kernel(TailArgs p)
         if (myrow) {
             double wv[5];
             TlWatch wd;
-            for (;;) {
-                bool ok = true;
+            if constexpr (VER == 1) {
+                for (;;) {
+                    bool ok = true;
 #pragma unroll
-                for (int e = 0; e < 5; ++e) {
-                    const int bb = lane + 32 * e;
-                    wv[e] = 0.0;
-                    if (bb < G) ok &= tl_try(p.W + (size_t)bb * TL_MAXROWS + rrow, tag, wv[e]);
+                    for (int e = 0; e < 5; ++e) {
+                        const int bb = lane + 32 * e;
+                        wv[e] = 0.0;
+                        if (bb < G) ok &= tl_try(p.W + (size_t)bb * TL_MAXROWS + rrow, tag, wv[e]);
+                    }
+                    if (lane == 0) ok &= tl_try(p.A1 + rrow, tag, a1r);
+                    if (__all_sync(0xffffffffu, ok)) break;
+                    wd.tick();
                 }
-                if (lane == 0) ok &= tl_try(p.A1 + rrow, tag, a1r);
-                if (__all_sync(0xffffffffu, ok)) break;
-                wd.tick();
+            } else {
+                unsigned pend = 0;                       // bit e: partial of CTA lane + 32 e, bit 5: a1 (lane 0)
+#pragma unroll
+                for (int e = 0; e < 5; ++e) { wv[e] = 0.0; if (lane + 32 * e < G) pend |= 1u << e; }
+                if (lane == 0) pend |= 1u << 5;
+                for (;;) {
+#pragma unroll
+                    for (int e = 0; e < 5; ++e)
+                        if ((pend >> e) & 1u) {
+                            double got;
+                            if (tl_try(p.W + (size_t)(lane + 32 * e) * TL_MAXROWS + rrow, tag, got)) { wv[e] = got; pend &= ~(1u << e); }
+                        }
+                    if ((pend >> 5) & 1u) {
+                        double got;
+                        if (tl_try(p.A1 + rrow, tag, got)) { a1r = got; pend &= ~(1u << 5); }
+                    }
+                    if (__all_sync(0xffffffffu, pend == 0)) break;
+                    wd.tick();
+                }
             }
             a1r = __shfl_sync(0xffffffffu, a1r, 0);
             acc = warp_sum(((wv[0] + wv[1]) + (wv[2] + wv[3])) + wv[4]);
@@ -297,7 +375,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) bidiag_tail_kernel(TailArgs p)
         __syncthreads();
         const double rr_tot = s_w[TL_WARPS], r1 = s_w[TL_WARPS + 1];
         Refl g;
-        if (has_row) g = make_refl(r1, rr_tot); else { g.snu = 0.0; g.inv = 0.0; }
+        if (has_row) g = tl_refl<VER>(r1, rr_tot); else { g.snu = 0.0; g.inv = 0.0; }
         const double u1 = (r1 + g.snu) * g.inv;
         if (b == 0 && t == 0) p.beta[i] = has_row ? -g.snu : r1;
         if (t < TL_CPC && t >= qlo_c && t < ncol) {
@@ -314,7 +392,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) bidiag_tail_kernel(TailArgs p)
         }
 
         // ---- next step's inputs: x (pending right update), c', c'.c'
-        {
+        if constexpr (VER == 1) {
             TlWatch wd;
             for (;;) {
                 bool ok = true;
@@ -328,6 +406,28 @@ __global__ void __launch_bounds__(TL_THREADS, 1) bidiag_tail_kernel(TailArgs p)
                     }
                 }
                 if (__all_sync(0xffffffffu, ok)) break;
+                wd.tick();
+            }
+        } else {
+            TlWatch wd;
+            unsigned pend = 0;                           // bit 2z: x of row t + 512 z, bit 2z+1: c'
+#pragma unroll
+            for (int z = 0; z < TL_RPT; ++z) {
+                const int rho = t + z * TL_THREADS;
+                xr[z] = 0.0; cr[z] = 0.0;
+                if (rho > lo && rho < L0) pend |= 3u << (2 * z);
+            }
+            for (;;) {
+#pragma unroll
+                for (int z = 0; z < TL_RPT; ++z) {
+                    const int rho = t + z * TL_THREADS;
+                    double got;
+                    if ((pend >> (2 * z)) & 1u)
+                        if (tl_try(p.X + rho, tag, got)) { xr[z] = got; pend &= ~(1u << (2 * z)); }
+                    if ((pend >> (2 * z + 1)) & 1u)
+                        if (tl_try(p.C + rho, tag, got)) { cr[z] = got; pend &= ~(2u << (2 * z)); }
+                }
+                if (__all_sync(0xffffffffu, pend == 0)) break;
                 wd.tick();
             }
         }

@@ -70,10 +70,12 @@ def test_bidiag_vs_golden_reference(D, name):
 @pytest.mark.parametrize("shape", [(1, 1), (2, 2), (3, 3), (5, 4), (33, 33), (64, 64), (200, 200), (513, 512),
                                    (300, 200), (97, 3), (40, 1), (1500, 1400), (2040, 1100), (2100, 2000),
                                    (2500, 2500)])
-def test_bidiag_on_chip_tail(D, shape, monkeypatch):
+# SVD_GPU_TAIL=2 (kernel version 2) is an experiment that is not the default: SVD_TEST_EXPERIMENTAL=1 adds it
+@pytest.mark.parametrize("tail", ["1"] + (["2"] if os.environ.get("SVD_TEST_EXPERIMENTAL") else []))
+def test_bidiag_on_chip_tail(D, shape, tail, monkeypatch):
     # bidiag_tail.cuh: once the trailing block fits the SMs' shared memory the rest of the factorization runs
     # in one cooperative launch (small inputs entirely, larger ones from the first panel boundary that fits)
-    monkeypatch.setenv("SVD_GPU_TAIL", "1")
+    monkeypatch.setenv("SVD_GPU_TAIL", tail)
     m, n = shape
     A = util.rand_matrix(m, n, 1.0, 2.0, 4)
     Ao, ao, bo = util.oracle_bidiag(A)
