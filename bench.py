@@ -9,7 +9,8 @@ the reference driver's input distribution; full U, Sigma, V).
           timed with CUDA events on the launching stream, K steps bracketed by barrier + synchronize).
   e2e   : seconds per step through the reference-facing call svd_gpu(m,n,A,sigma,U,V) with pinned HOST
           buffers; host->device and device->host copies are inside the timed region.
-  roofline     : the bidiagonalization's streaming passes (gemvT/gemvN), HBM bound.
+  roofline     : the bidiagonalization (fused single-read pass + finish + panel GEMM, on-chip tail), HBM bound;
+                 the back-transform's DMMA rate and single full-size pass probes ride along.
   cpu_baseline : the reference's own CPU path (oracle/_ref, else the oracle port) on a bounded sample.
 N > 1 (torchrun): bidiagonalization + dDC on rank 0, NCCL broadcast of reflectors / bidiagonal /
 singular values, twisted vectors + back-transform sharded by singular-value blocks, NCCL all-gather of

@@ -26,7 +26,7 @@ constexpr int TL_WARPS = TL_THREADS / 32;
 constexpr int TL_RPT = 4;                         // rows per thread
 constexpr int TL_MAXROWS = TL_THREADS * TL_RPT;   // 2048
 constexpr int TL_CPC = 16;                        // columns per CTA (register arrays)
-constexpr int TL_MAXG = 148;                      // CTAs (= partial vectors; tmpN has that many rows; <= 160: 5 per lane)
+constexpr int TL_MAXG = 148;                      // CTAs (= partial vectors per row; <= 160: 5 per lane)
 constexpr int TL_CAP = 28000;                     // doubles of shared memory for the matrix (224 KB)
 constexpr int TL_AUX = 4 * TL_CPC + TL_WARPS * (TL_CPC + 1) + 64;
 
