@@ -131,6 +131,9 @@ tw_select_kernel(int mb, int ns, const double *__restrict__ tau, const double *_
 // (TwistedFactorization, parallel-twisted.c:495-521).  z overwrites S in place.
 // All lanes walk the SAME rows (coalesced, loads batched 8 rows ahead of the serial recurrence);
 // a lane simply stays idle (z = 1) until the walk reaches its own twist index.
+// UB = rows whose loads are in flight ahead of the recurrence (8 by default; SVD_GPU_TW_UB=16/32 is an experiment:
+// 128 warps x 8 x 256 B in flight cannot cover the HBM latency at n = 4096)
+template <int UB>
 __global__ void __launch_bounds__(32)
 tw_solve_kernel(int mb, int ns, const double *__restrict__ q, const double *__restrict__ e,
                 const double *__restrict__ ab, const double *__restrict__ pivmin_p,
@@ -143,7 +146,6 @@ tw_solve_kernel(int mb, int ns, const double *__restrict__ q, const double *__re
     const int k = kidx[t];
     const double pivmin = *pivmin_p;
     double z = 1.0, acc = 0.0;
-    constexpr int UB = 8;
     if (blockIdx.y == 0) {
         // downward: rows kmax-1 .. 0 (warp-uniform start), a lane is active where j < k
         const int kmax = __reduce_max_sync(0xffffffffu, k);
@@ -292,6 +294,14 @@ tw_left_finalize_kernel(int n, int ns, const double *__restrict__ Z, const doubl
     }
 }
 
+static void launch_tw_solve(int ub, dim3 grid, cudaStream_t st, int mb, int ns, const double *q, const double *e,
+                            const double *ab, const double *pivmin, const int *kidx, double *S, const double *P, double *nrm2)
+{
+    if (ub == 32) tw_solve_kernel<32><<<grid, 32, 0, st>>>(mb, ns, q, e, ab, pivmin, kidx, S, P, nrm2);
+    else if (ub == 16) tw_solve_kernel<16><<<grid, 32, 0, st>>>(mb, ns, q, e, ab, pivmin, kidx, S, P, nrm2);
+    else tw_solve_kernel<8><<<grid, 32, 0, st>>>(mb, ns, q, e, ab, pivmin, kidx, S, P, nrm2);
+}
+
 static int tw_chunk(int mb, int ns)
 {
     const size_t budget = (size_t)4 << 30;                 // bytes for the two scratch panels
@@ -336,6 +346,8 @@ void twisted_vectors_device(int n, int mb, const double *a, const double *b, con
     tw_prep_kernel<<<1, 1024, 0, st>>>(n, mb, a, b, q, e, ab, pivmin);
     SVD_KERNEL_CHECK();
     // left vectors from their own twisted factorization when B is square (SVD_GPU_LEFT=bx restores y = Bx/sigma)
+    const char *uenv = getenv("SVD_GPU_TW_UB");
+    const int tw_ub = uenv ? atoi(uenv) : 8;
     const char *lenv = getenv("SVD_GPU_LEFT");
     const bool left_by_twist = (Y != nullptr) && (mb == n) && (n > 1) && !(lenv && lenv[0] == 'b');
     if (left_by_twist) {
@@ -352,7 +364,7 @@ void twisted_vectors_device(int n, int mb, const double *a, const double *b, con
             SVD_KERNEL_CHECK();
             tw_select_kernel<<<ceil_div(c, 32), 32 * TWS_SL, 0, st>>>(mb, c, tau, S, P, kidx, gk);
             SVD_KERNEL_CHECK();
-            tw_solve_kernel<<<dim3(ceil_div(c, 32), 2), 32, 0, st>>>(mb, c, q, e, ab, pivmin, kidx, S, P, nrm2);
+            launch_tw_solve(tw_ub, dim3(ceil_div(c, 32), 2), st, mb, c, q, e, ab, pivmin, kidx, S, P, nrm2);
             SVD_KERNEL_CHECK();
             if (sweep < rqi_steps) {
                 tw_rqi_kernel<<<ceil_div(c, 256), 256, 0, st>>>(c, gi0, ntot, sigma_all, gk, nrm2, tau);
@@ -371,7 +383,7 @@ void twisted_vectors_device(int n, int mb, const double *a, const double *b, con
             SVD_KERNEL_CHECK();
             tw_select_kernel<<<ceil_div(c, 32), 32 * TWS_SL, 0, st>>>(n, c, tau, S, P, kidx, gk);
             SVD_KERNEL_CHECK();
-            tw_solve_kernel<<<dim3(ceil_div(c, 32), 2), 32, 0, st>>>(n, c, q2, e2, ab2, pivmin, kidx, S, P, nrm2);
+            launch_tw_solve(tw_ub, dim3(ceil_div(c, 32), 2), st, n, c, q2, e2, ab2, pivmin, kidx, S, P, nrm2);
             SVD_KERNEL_CHECK();
             tw_left_sign_kernel<<<ceil_div(c, 256), 256, 0, st>>>(n, c, a, b, kidx, Xc, ldx, gk);
             SVD_KERNEL_CHECK();
