@@ -94,7 +94,8 @@ tw_qd_kernel(int mb, int ns, const double *__restrict__ q, const double *__restr
 // gamma_j = s_j + p_j + tau; twist index = argmin |gamma_j|, later index on ties
 // (which_min_gamma, parallel-twisted.c:277-284).  32 sigmas (lanes) x 8 position slices (warps);
 // every slice scans its positions with coalesced loads, the slices are merged in a fixed order.
-constexpr int TWS_SL = 8;
+// TWS_SL position slices per CTA: 8 by default; SVD_GPU_TW_SL=32 is an experiment (more loads in flight)
+template <int TWS_SL>
 __global__ void __launch_bounds__(32 * TWS_SL)
 tw_select_kernel(int mb, int ns, const double *__restrict__ tau, const double *__restrict__ S,
                  const double *__restrict__ P, int *__restrict__ kidx, double *__restrict__ gk)
@@ -294,6 +295,14 @@ tw_left_finalize_kernel(int n, int ns, const double *__restrict__ Z, const doubl
     }
 }
 
+static void launch_tw_select(int sl, int grid, cudaStream_t st, int mb, int ns, const double *tau, const double *S,
+                             const double *P, int *kidx, double *gk)
+{
+    if (sl == 32) tw_select_kernel<32><<<grid, 32 * 32, 0, st>>>(mb, ns, tau, S, P, kidx, gk);
+    else if (sl == 16) tw_select_kernel<16><<<grid, 32 * 16, 0, st>>>(mb, ns, tau, S, P, kidx, gk);
+    else tw_select_kernel<8><<<grid, 32 * 8, 0, st>>>(mb, ns, tau, S, P, kidx, gk);
+}
+
 static void launch_tw_solve(int ub, dim3 grid, cudaStream_t st, int mb, int ns, const double *q, const double *e,
                             const double *ab, const double *pivmin, const int *kidx, double *S, const double *P, double *nrm2)
 {
@@ -348,6 +357,8 @@ void twisted_vectors_device(int n, int mb, const double *a, const double *b, con
     // left vectors from their own twisted factorization when B is square (SVD_GPU_LEFT=bx restores y = Bx/sigma)
     const char *uenv = getenv("SVD_GPU_TW_UB");
     const int tw_ub = uenv ? atoi(uenv) : 8;
+    const char *senv = getenv("SVD_GPU_TW_SL");
+    const int tw_sl = senv ? atoi(senv) : 8;
     const char *lenv = getenv("SVD_GPU_LEFT");
     const bool left_by_twist = (Y != nullptr) && (mb == n) && (n > 1) && !(lenv && lenv[0] == 'b');
     if (left_by_twist) {
@@ -362,7 +373,7 @@ void twisted_vectors_device(int n, int mb, const double *a, const double *b, con
         for (int sweep = 0; sweep <= rqi_steps; ++sweep) {
             tw_qd_kernel<<<dim3(ceil_div(c, 32), 2), 32, 0, st>>>(mb, c, q, e, tau, pivmin, S, P);
             SVD_KERNEL_CHECK();
-            tw_select_kernel<<<ceil_div(c, 32), 32 * TWS_SL, 0, st>>>(mb, c, tau, S, P, kidx, gk);
+            launch_tw_select(tw_sl, ceil_div(c, 32), st, mb, c, tau, S, P, kidx, gk);
             SVD_KERNEL_CHECK();
             launch_tw_solve(tw_ub, dim3(ceil_div(c, 32), 2), st, mb, c, q, e, ab, pivmin, kidx, S, P, nrm2);
             SVD_KERNEL_CHECK();
@@ -381,7 +392,7 @@ void twisted_vectors_device(int n, int mb, const double *a, const double *b, con
             // y_i from B B^T - sigma_i^2 I (reversed bidiagonal), with the polished sigma_i^2 already in tau
             tw_qd_kernel<<<dim3(ceil_div(c, 32), 2), 32, 0, st>>>(n, c, q2, e2, tau, pivmin, S, P);
             SVD_KERNEL_CHECK();
-            tw_select_kernel<<<ceil_div(c, 32), 32 * TWS_SL, 0, st>>>(n, c, tau, S, P, kidx, gk);
+            launch_tw_select(tw_sl, ceil_div(c, 32), st, n, c, tau, S, P, kidx, gk);
             SVD_KERNEL_CHECK();
             launch_tw_solve(tw_ub, dim3(ceil_div(c, 32), 2), st, n, c, q2, e2, ab2, pivmin, kidx, S, P, nrm2);
             SVD_KERNEL_CHECK();
