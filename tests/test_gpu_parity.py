@@ -431,6 +431,49 @@ def test_svd_gpu_gemm_kernels_agree(D, shape, monkeypatch):
         assert np.all(np.abs(np.sum(V0[:, sep] * V1[:, sep], axis=0)) >= 1 - 1e-8)
 
 
+@pytest.mark.skipif(not os.environ.get("SVD_TEST_EXPERIMENTAL"),
+                    reason="written without a GPU at hand: enable with SVD_TEST_EXPERIMENTAL=1, un-gate once it has run")
+@pytest.mark.parametrize("shape,world", [((900, 900), 3), ((1200, 700), 2), ((2304, 2304), 4)])
+def test_sharded_entry_points_on_one_gpu(D, shape, world):
+    # SURVEY 8e on a single device: svd_gpu_values_dev (what rank 0 runs), then svd_gpu_vectors_dev once per
+    # "rank" for its block of singular values (ddc_svd_b200/sharding.py:shard_range) - the concatenated blocks
+    # must be the SVD, and the polished singular values must come back block by block
+    from ddc_svd_b200.sharding import shard_range
+    m, n = shape
+    mn = min(m, n)
+    L = D.lib()
+    A = util.rand_matrix(m, n)
+    Af = np.asfortranarray(A)
+    bufs = []
+
+    def dev(nbytes):
+        d = L.svdgpu_malloc(nbytes); bufs.append(d)
+        L.svdgpu_memset(d, 0, nbytes, None)
+        return d
+    try:
+        dA = dev(Af.nbytes)
+        L.svdgpu_h2d(dA, util.p(Af), Af.nbytes, None)
+        dal, dbe, dsg = dev(8 * mn), dev(8 * (mn + 1)), dev(8 * mn)
+        L.svd_gpu_values_dev(m, n, dA, m, dal, dbe, dsg, None)
+        U = np.zeros((m, mn), order="F"); V = np.zeros((n, mn), order="F"); sig = np.zeros(mn)
+        for rank in range(world):
+            blk, i0, ns = shard_range(mn, world, rank)
+            if ns == 0:
+                continue
+            dU, dV, dso = dev(8 * m * blk), dev(8 * n * blk), dev(8 * blk)
+            L.svd_gpu_vectors_dev(m, n, dA, m, dal, dbe, dsg, i0, ns, dU, m, dV, n, dso, None)
+            Ub = np.zeros((m, ns), order="F"); Vb = np.zeros((n, ns), order="F"); sb = np.zeros(ns)
+            L.svdgpu_d2h(util.p(Ub), dU, Ub.nbytes, None)
+            L.svdgpu_d2h(util.p(Vb), dV, Vb.nbytes, None)
+            L.svdgpu_d2h(util.p(sb), dso, sb.nbytes, None)
+            L.svdgpu_stream_sync(None)
+            U[:, i0:i0 + ns] = Ub; V[:, i0:i0 + ns] = Vb; sig[i0:i0 + ns] = sb
+    finally:
+        for d in bufs:
+            L.svdgpu_free(d)
+    check_lapack_bounds(A, sig, U, V)
+
+
 # ------------------------------------------------------------------ QR first (m >> n)
 @pytest.mark.parametrize("shape", [(5, 2), (300, 100), (1025, 33), (5000, 257), (70000, 130), (4097, 512)])
 def test_qr_tall_vs_lapack(D, shape):
