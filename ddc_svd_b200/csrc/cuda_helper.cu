@@ -36,7 +36,7 @@ void svdgpu_set_device(int dev) { SVD_CUDA_CHECK(cudaSetDevice(dev)); }
 int svdgpu_get_device(void) { int d = 0; SVD_CUDA_CHECK(cudaGetDevice(&d)); return d; }
 const char *svdgpu_device_name(void)
 {
-    static char name[256];
+    static char name[320];
     cudaDeviceProp p;
     SVD_CUDA_CHECK(cudaGetDeviceProperties(&p, svdgpu_get_device()));
     snprintf(name, sizeof name, "%s (sm_%d%d, %d SMs)", p.name, p.major, p.minor, p.multiProcessorCount);
