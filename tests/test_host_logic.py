@@ -129,3 +129,18 @@ def test_on_chip_tail_planning():
     assert f(200, 300, 32, 148) == 200                                  # wide inputs never (they arrive transposed)
     assert f(65536, 4096, 32, 148) == 4096                              # too tall: 61k rows never fit
     assert f(4096, 4096, 32, 8) == 4096 - 128                           # fewer CTAs: 8 x 16 columns at most
+
+
+@pytest.mark.parametrize("shape,i0,G", [((1, 1), 0, 3), ((3, 3), 0, 5), ((30, 28), 0, 5), ((60, 60), 0, 7),
+                                        ((64, 64), 0, 4), ((97, 3), 0, 6), ((40, 1), 0, 2), ((80, 70), 0, 11)])
+def test_on_chip_tail_model_matches_oracle(shape, i0, G):
+    # tests/model_tail.py is the numpy specification bidiag_tail_kernel was written from: same column
+    # distribution, same phases, same exchanged buffers; it must reproduce the reference's bidiagonalization
+    import model_tail
+    m, n = shape
+    A = util.rand_matrix(m, n, 1.0, 2.0, 4)
+    Ao, ao, bo = util.oracle_bidiag(A)
+    Ag, ag, bg = model_tail.tail_model(A, i0, G)
+    assert np.abs(Ag - Ao).max() <= 1e-11 and np.abs(ag - ao).max() <= 1e-11
+    if n > 1:
+        assert np.abs(bg - bo).max() <= 1e-11
