@@ -1,7 +1,10 @@
 """Small end-to-end calls for compute-sanitizer (not a pytest file):
     compute-sanitizer --tool memcheck python tests/sanitize_target.py
 Covers the fused pass (clusters of 1 and 2 via SVD_GPU_FUSED_CS), the split passes, QR first, the
-wide-as-transpose route, values only, and the phase entry points."""
+wide-as-transpose route, values only, the phase entry points, and - second loop - the kernels behind the
+SVD_GPU_TAIL / SVD_GPU_GEMM_WS switches (on-chip tail on and off, persistent and one-tile-per-CTA GEMM).
+(racecheck does not follow cross-CTA traffic through global memory: the tail kernel's exchange protocol is
+argued in bidiag_tail.cuh and exercised by test_bidiag_on_chip_tail.)"""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -18,6 +21,15 @@ for (m, n) in [(300, 300), (700, 120), (120, 700), (513, 257), (64, 64), (1, 1),
     s2, _, _, _ = D.svd_gpu(A, vectors=False)
     assert np.abs(s2 - s).max() <= 10 * EPS * max(m, n) * max(s.max(), 1.0)
     print("svd_gpu", (m, n), "ok", flush=True)
+for tail, ws in (("0", "1"), ("1", "0"), ("0", "0")):
+    os.environ["SVD_GPU_TAIL"] = tail; os.environ["SVD_GPU_GEMM_WS"] = ws
+    for (m, n) in [(300, 300), (700, 120), (257, 513)]:
+        A = util.rand_matrix(m, n)
+        s, U, V, _ = D.svd_gpu(A)
+        met = util.svd_metrics(A, s, U, V)
+        assert met["resid"] <= 100 * EPS * max(m, n), (tail, ws, m, n, met)
+    print("svd_gpu with SVD_GPU_TAIL=%s SVD_GPU_GEMM_WS=%s ok" % (tail, ws), flush=True)
+del os.environ["SVD_GPU_TAIL"], os.environ["SVD_GPU_GEMM_WS"]
 A = util.rand_matrix(400, 350)
 Am, al, be = D.bidiag_par(A)
 Ao, ao, bo = util.oracle_bidiag(A)
