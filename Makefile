@@ -1,7 +1,8 @@
 # Top-level build: the product library (sm_100a only), the test oracle, and the drop-in client.
 #   make            -> ddc_svd_b200/libsvdgpu.so
 #   make oracle     -> oracle/libddcoracle.so (+ oracle/_ref/libddcref.so when /root/reference exists)
-#   make dropin     -> build/test-whole-svd from the reference's UNMODIFIED driver source
+#   make dropin     -> build/test-whole-svd from the reference's UNMODIFIED driver source, and build/dropin_check
+#                      (tests/dropin_check.c: the same flow with the driver's dormant check enabled)
 NVCC      ?= nvcc
 CC         = gcc
 ARCH       = -gencode arch=compute_100a,code=sm_100a
@@ -27,7 +28,7 @@ build/obj/host_%.o: $(PKG)/host/%.c $(HDRS)
 	$(CC) $(CFLAGS) -c $< -o $@
 
 $(LIB): $(CU_OBJS) $(C_OBJS)
-	$(NVCC) $(ARCH) -shared -o $@ $^ -lcudart
+	$(NVCC) $(ARCH) -shared -o $@ $^ -lcudart -ldl -lpthread
 
 oracle:
 	$(MAKE) -C oracle all
@@ -41,6 +42,8 @@ dropin: $(LIB)
 	  $(CC) -std=gnu99 -O2 -Iinclude -o build/test-whole-svd -x c - < $(REF)/test-whole-svd.c \
 	        -L$(PKG) -lsvdgpu -Wl,-rpath,'$$ORIGIN/../$(PKG)' -lm && echo built build/test-whole-svd; \
 	else echo "dropin: $(REF)/test-whole-svd.c not present"; fi
+	$(CC) -std=gnu99 -O2 -Iinclude -o build/dropin_check tests/dropin_check.c \
+	      -L$(PKG) -lsvdgpu -Wl,-rpath,'$$ORIGIN/../$(PKG)' -lm && echo built build/dropin_check
 
 clean:
 	rm -rf build $(LIB)

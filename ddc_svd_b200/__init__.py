@@ -25,6 +25,8 @@ _lib = None
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_float_p = ctypes.POINTER(ctypes.c_float)
 c_void_p = ctypes.c_void_p
+c_void_pp = ctypes.POINTER(ctypes.c_void_p)
+c_int_p = ctypes.POINTER(ctypes.c_int)
 c_int, c_long, c_size_t, c_double = ctypes.c_int, ctypes.c_long, ctypes.c_size_t, ctypes.c_double
 
 # (name, restype, argtypes) for every symbol include/*.h declares
@@ -38,6 +40,21 @@ SIGNATURES = [
     ("svd_gpu_values_dev", None, [c_int, c_int, c_void_p, c_long, c_void_p, c_void_p, c_void_p, c_void_p]),
     ("svd_gpu_last_phase_ms", None, [c_float_p]),
     ("svd_gpu_set_option", None, [ctypes.c_char_p, c_int]),
+    ("svdgpu_group_create_local", c_void_p, [c_int, c_int_p]),
+    ("svdgpu_group_create_rank", c_void_p, [c_int, c_int, c_void_p]),
+    ("svdgpu_group_destroy", None, [c_void_p]),
+    ("svdgpu_group_size", c_int, [c_void_p]),
+    ("svdgpu_group_nlocal", c_int, [c_void_p]),
+    ("svdgpu_group_rank", c_int, [c_void_p, c_int]),
+    ("svdgpu_group_device", c_int, [c_void_p, c_int]),
+    ("svdgpu_shard_range", None, [c_int, c_int, c_int, c_int_p, c_int_p, c_int_p]),
+    ("svd_gpu_sharded_dev", None, [c_void_p, c_int, c_int, c_void_p, c_long, c_void_pp, c_void_pp, c_long,
+                                   c_void_pp, c_long, c_void_pp]),
+    ("svd_gpu_sharded", None, [c_void_p, c_int, c_int, c_double_p, c_double_p, c_void_pp, c_void_pp]),
+    ("svd_gpu_group_phase_ms", None, [c_void_p, c_int, c_float_p]),
+    ("svd_gpu_check", None, [c_int, c_int, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
+    ("svd_gpu_check_dev", None, [c_int, c_int, c_void_p, c_long, c_void_p, c_void_p, c_long, c_void_p, c_long,
+                                 c_int, c_double_p, c_void_p]),
     # include/bidiag_par.h
     ("bidiag_par", None, [c_int, c_int, c_double_p, c_double_p, c_double_p]),
     ("form_u_par", None, [c_int, c_int, c_double_p, c_double_p]),
@@ -78,6 +95,23 @@ SIGNATURES = [
     ("svdgpu_h2d_2d", None, [c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_size_t, c_void_p]),
     ("svdgpu_d2h_2d", None, [c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_size_t, c_void_p]),
     ("svdgpu_stream_create", c_void_p, []),
+    ("svdgpu_stream_create_priority", c_void_p, [c_int]),
+    ("svdgpu_host_register", c_int, [c_void_p, c_size_t]),
+    ("svdgpu_host_unregister", None, [c_void_p]),
+    ("svdgpu_device_sync", None, []),
+    ("svdgpu_enable_peer_access", c_int, [c_int, c_int]),
+    ("svdgpu_range_push", None, [ctypes.c_char_p]),
+    ("svdgpu_range_pop", None, []),
+    ("svdgpu_nccl_version", c_int, []),
+    ("svdgpu_nccl_unique_id", None, [c_void_p]),
+    ("svdgpu_nccl_comm_init_rank", c_void_p, [c_int, c_int, c_void_p]),
+    ("svdgpu_nccl_comm_init_all", None, [c_int, c_int_p, c_void_pp]),
+    ("svdgpu_nccl_comm_destroy", None, [c_void_p]),
+    ("svdgpu_nccl_comm_count", c_int, [c_void_p]),
+    ("svdgpu_nccl_group_start", None, []),
+    ("svdgpu_nccl_group_end", None, []),
+    ("svdgpu_nccl_bcast", None, [c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
+    ("svdgpu_nccl_allgather", None, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     ("svdgpu_stream_destroy", None, [c_void_p]),
     ("svdgpu_stream_sync", None, [c_void_p]),
     ("svdgpu_stream_wait_event", None, [c_void_p, c_void_p]),
@@ -90,6 +124,8 @@ SIGNATURES = [
     ("svdgpu_host_free", None, [c_void_p]),
     ("svdgpu_bidiag_workspace", c_size_t, [c_int, c_int, c_long]),
     ("svdgpu_bidiag", None, [c_int, c_int, c_void_p, c_long, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    ("svdgpu_bidiag_progress", None, [c_int, c_int, c_void_p, c_long, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                      c_void_p]),
     ("svdgpu_bidiag_tail_start", c_int, [c_int, c_int, c_int, c_int]),
     ("svdgpu_ddc_workspace", c_size_t, [c_int]),
     ("svdgpu_ddc_values", None, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -101,6 +137,18 @@ SIGNATURES = [
     ("svdgpu_qr_workspace", c_size_t, [c_int, c_int]),
     ("svdgpu_qr", None, [c_int, c_int, c_void_p, c_long, c_void_p, c_long, c_void_p, c_void_p]),
     ("svdgpu_wy_apply", None, [c_int, c_int, c_int, c_void_p, c_long, c_void_p, c_long, c_int, c_void_p, c_void_p]),
+    ("svdgpu_qr_progress", None, [c_int, c_int, c_void_p, c_long, c_void_p, c_long, c_void_p, c_void_p, c_void_p]),
+    ("svdgpu_wy_panel_width", c_int, []),
+    ("svdgpu_wy_panel_count", c_int, [c_int]),
+    ("svdgpu_wy_panels_bytes", c_size_t, [c_int, c_int]),
+    ("svdgpu_wy_apply_workspace", c_size_t, [c_int]),
+    ("svdgpu_wy_setup", None, [c_int, c_int, c_int, c_void_p, c_long, c_void_p, c_int, c_int, c_void_p]),
+    ("svdgpu_wy_apply_prepared", None, [c_int, c_int, c_int, c_void_p, c_void_p, c_long, c_int, c_void_p, c_void_p]),
+    ("svdgpu_wy_panel_slices", None, [c_void_p, c_int, c_int, c_int, c_int, c_void_pp, c_void_pp,
+                                      ctypes.POINTER(c_size_t)]),
+    ("svdgpu_check_workspace", c_size_t, [c_int, c_int, c_int]),
+    ("svdgpu_check", None, [c_int, c_int, c_void_p, c_long, c_void_p, c_void_p, c_long, c_void_p, c_long, c_int,
+                            c_void_p, c_void_p, c_void_p]),
     ("svdgpu_dgemm", None, [c_int, c_int, c_int, c_int, c_int, c_double, c_void_p, c_long, c_void_p, c_long,
                             c_double, c_void_p, c_long, c_void_p]),
     ("svdgpu_scale_matrix", None, [c_int, c_int, c_void_p, c_long, c_void_p, c_void_p, c_void_p]),
@@ -243,6 +291,89 @@ def qr_tall(A):
         for d in (dA, dR, dQ, work):
             L.svdgpu_free(d)
     return A_qr, R, Q1
+
+
+def shard_range(mn, world, rank):
+    """(blk, i0, ns) of rank's block of singular values (svdgpu_shard_range)."""
+    b, i0, ns = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    lib().svdgpu_shard_range(mn, world, rank, ctypes.byref(b), ctypes.byref(i0), ctypes.byref(ns))
+    return b.value, i0.value, ns.value
+
+
+class Group:
+    """A group of ranks, one per GPU (include/svd_gpu_b200.h).  Group.local(n) drives n GPUs from this
+    process; Group.rank(world, rank, id128) is one rank of a one-process-per-GPU job (id128 = the 128 bytes
+    Group.unique_id() returns on rank 0, shared out of band, e.g. with torch.distributed.broadcast)."""
+
+    def __init__(self, handle):
+        self.h = handle
+
+    @staticmethod
+    def unique_id():
+        buf = ctypes.create_string_buffer(128)
+        lib().svdgpu_nccl_unique_id(buf)
+        return buf.raw
+
+    @classmethod
+    def local(cls, ndev, devices=None):
+        arr = (ctypes.c_int * ndev)(*devices) if devices is not None else None
+        return cls(lib().svdgpu_group_create_local(ndev, arr))
+
+    @classmethod
+    def rank(cls, world, rank, id128):
+        buf = ctypes.create_string_buffer(bytes(id128), 128)
+        return cls(lib().svdgpu_group_create_rank(world, rank, buf))
+
+    @property
+    def world(self):
+        return lib().svdgpu_group_size(self.h)
+
+    @property
+    def nlocal(self):
+        return lib().svdgpu_group_nlocal(self.h)
+
+    def global_rank(self, local):
+        return lib().svdgpu_group_rank(self.h, local)
+
+    def phase_ms(self, local=0):
+        ms = (ctypes.c_float * 8)()
+        lib().svd_gpu_group_phase_ms(self.h, local, ms)
+        return list(ms)
+
+    def destroy(self):
+        if self.h:
+            lib().svdgpu_group_destroy(self.h)
+            self.h = None
+
+    def svd(self, A):
+        """svd_gpu_sharded on a host matrix with a LOCAL group: returns (sigma, U, V, A_mod), every rank's
+        column block copied from its own GPU into place."""
+        Af = _colmajor(A)
+        m, n = Af.shape
+        mn = min(m, n)
+        sigma = np.zeros(mn)
+        U = np.zeros((m, mn), order="F")
+        V = np.zeros((n, mn), order="F")
+        nl = self.nlocal
+        ub = (ctypes.c_void_p * nl)()
+        vb = (ctypes.c_void_p * nl)()
+        for lr in range(nl):
+            _, i0, _ = shard_range(mn, self.world, self.global_rank(lr))
+            ub[lr] = U.ctypes.data + 8 * i0 * m
+            vb[lr] = V.ctypes.data + 8 * i0 * n
+        lib().svd_gpu_sharded(self.h, m, n, _p(Af), _p(sigma), ub, vb)
+        return sigma, U, V, Af
+
+
+def check(A, sigma, U, V):
+    """svd_gpu_check: the reference driver's dormant residual check (test-whole-svd.c:81-96) run on the GPU.
+    Returns dict(orthU, orthV, resid, checksum, normA, ascending)."""
+    A0 = _colmajor(A)
+    m, n = A0.shape
+    out = np.zeros(6)
+    lib().svd_gpu_check(m, n, _p(A0), _p(np.ascontiguousarray(sigma, dtype=np.float64)),
+                        _p(_colmajor(U)), _p(_colmajor(V)), _p(out))
+    return dict(orthU=out[0], orthV=out[1], resid=out[2], checksum=out[3], normA=out[4], ascending=bool(out[5] == 1.0))
 
 
 def last_phase_ms():

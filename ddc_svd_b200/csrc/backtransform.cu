@@ -15,30 +15,32 @@
 // Flop count is the reference's 4*(m-j) per reflector per vector, but as BLAS3.
 #include "common.cuh"
 #include "backtransform.cuh"
+#include "bidiag.cuh"
 
 namespace svdgpu {
 
 constexpr int NBW = 128;    // WY panel width (K of the update GEMM: 128 keeps it DMMA-bound, not C-traffic-bound)
 
-// VL[r, j] = A[r, j] for r >= j (left reflector j lives in column j from the diagonal down)
-__global__ void extract_left_kernel(int m, int nL, int nLpad, const double *__restrict__ A, long lda,
+// VL[r, jj] = A[r, j0 + jj] for r >= j0 + jj (left reflector j lives in column j from the diagonal down);
+// columns [j0, j0 + ncols) of the gathered array, VL already offset to column j0
+__global__ void extract_left_kernel(int m, int nL, int j0, int ncols, const double *__restrict__ A, long lda,
                                     double *__restrict__ VL, long ldv)
 {
     long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long)ldv * nLpad) return;
-    int r = (int)(idx % ldv), j = (int)(idx / ldv);
+    if (idx >= (long)ldv * ncols) return;
+    int r = (int)(idx % ldv), j = j0 + (int)(idx / ldv);
     double v = 0.0;
     if (j < nL && r < m && r >= j) v = A[r + (long)j * lda];
     VL[idx] = v;
 }
 
-// VR[c, j] = A[j, c] for c >= j+1 (right reflector j lives in row j right of the super-diagonal)
+// VR[c, jj] = A[j0 + jj, c] for c >= j0 + jj + 1 (right reflector j lives in row j right of the super-diagonal)
 __global__ void __launch_bounds__(256)
-extract_right_kernel(int n, int nR, int nRpad, const double *__restrict__ A, long lda,
+extract_right_kernel(int n, int nR, int jbase, int ncols, const double *__restrict__ A, long lda,
                      double *__restrict__ VR, long ldv)
 {
     __shared__ double tile[32][33];
-    const int c0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+    const int c0 = blockIdx.x * 32, j0 = jbase + blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     for (int q = ty; q < 32; q += 8) {          // read A[j0+tx, c0+q] : rows contiguous over tx
         int j = j0 + tx, c = c0 + q;
@@ -47,9 +49,9 @@ extract_right_kernel(int n, int nR, int nRpad, const double *__restrict__ A, lon
         tile[q][tx] = v;
     }
     __syncthreads();
-    for (int q = ty; q < 32; q += 8) {          // write VR[c0+tx, j0+q]
+    for (int q = ty; q < 32; q += 8) {          // write VR[c0+tx, j0+q-jbase]
         int c = c0 + tx, j = j0 + q;
-        if (c < ldv && j < nRpad) VR[c + (long)j * ldv] = (c < n) ? tile[tx][q] : 0.0;
+        if (c < ldv && j - jbase < ncols) VR[c + (long)(j - jbase) * ldv] = (c < n) ? tile[tx][q] : 0.0;
     }
 }
 
@@ -100,85 +102,137 @@ static int pick_split(int tiles, int K, int nsm)
     return best;
 }
 
+// ---- storage of the prepared panels of one reflector set: V | VT | G | T -----------------------
+struct WyPanels { double *V, *VT, *G, *T; long ld; int npad, np; };
+static WyPanels wy_carve(void *panels, int rows, int nref)
+{
+    WyPanels w;
+    w.ld = round_up(rows, 2);
+    w.npad = (int)round_up(nref > 0 ? nref : 1, NBW);
+    w.np = w.npad / NBW;
+    double *p = (double *)panels;
+    w.V = p;   p += (size_t)w.ld * w.npad;
+    w.VT = p;  p += (size_t)w.ld * w.npad;
+    w.G = p;   p += (size_t)w.np * NBW * NBW;
+    w.T = p;
+    return w;
+}
+int wy_panel_count(int nref) { return (int)(round_up(nref > 0 ? nref : 1, NBW) / NBW); }
+int wy_panel_width() { return NBW; }
+size_t wy_panels_bytes(int rows, int nref)
+{
+    const long ld = round_up(rows, 2), npad = round_up(nref > 0 ? nref : 1, NBW), np = npad / NBW;
+    return (2 * (size_t)ld * npad + 2 * (size_t)np * NBW * NBW) * sizeof(double) + 256;
+}
+// the part of the panel storage other devices need for wy_apply_prepared: columns [pb*NBW, pe*NBW) of V and of VT
+void wy_panel_slices(void *panels, int rows, int nref, int pb, int pe, double **V, double **VT, size_t *count)
+{
+    const WyPanels w = wy_carve(panels, rows, nref);
+    *V = w.V + (size_t)pb * NBW * w.ld;
+    *VT = w.VT + (size_t)pb * NBW * w.ld;
+    *count = (size_t)(pe - pb) * NBW * w.ld;
+}
+size_t wy_apply_workspace_bytes(int nc)
+{
+    return ((size_t)NBW * nc + (size_t)WY_MAX_SPLIT * NBW * nc) * sizeof(double) + 256;
+}
 size_t backtransform_workspace_bytes(int rows, int nref, int nc)
 {
-    long ld = round_up(rows, 2);
-    long npad = round_up(nref > 0 ? nref : 1, NBW);
-    long np = npad / NBW;
-    size_t d = 0;
-    d += 2 * (size_t)ld * npad;                 // V, VT
-    d += 2 * (size_t)np * NBW * NBW;            // G, T
-    d += (size_t)NBW * nc;                      // W
-    d += (size_t)WY_MAX_SPLIT * NBW * nc;       // split-K partials
-    return d * sizeof(double) + 4096;
+    return wy_panels_bytes(rows, nref) + wy_apply_workspace_bytes(nc) + 4096;
 }
 
-// Apply Q = H_0 H_1 ... H_{nref-1} to C (rows x nc, ldc) in place.  Reflector j is
-// column j of the (rows x nref) trapezoid described by `left`:
+// Prepare panels [pb, pe) of a reflector set: gather the reflectors into column form (V), Gram matrices,
+// T = (striu(V^T V) + I/2)^-1 and VT = V T.  Reflector j is column j of the (rows x nref) trapezoid described
+// by `left`:
 //   left = 1: v_j = A[j:rows, j]        (column reflectors, rows = m)
 //   left = 0: v_j = A[j, j+1:rows]^T    (row reflectors,    rows = n)
-void wy_apply_device(int left, int rows, int nref, const double *A, long lda, double *C, long ldc, int nc,
-                     void *workspace, cudaStream_t st)
+// Only reflectors [pb*NBW, pe*NBW) of A have to be final, so the panels can be prepared while the
+// factorization that produces the later ones is still running (and shipped to other devices).
+void wy_setup_device(int left, int rows, int nref, const double *A, long lda, void *panels, int pb, int pe,
+                     cudaStream_t st)
 {
-    if (nref <= 0 || nc <= 0) return;
-    const long ld = round_up(rows, 2);
-    const int npad = (int)round_up(nref, NBW), np = npad / NBW;
+    if (nref <= 0) return;
+    const WyPanels w = wy_carve(panels, rows, nref);
+    if (pe > w.np) pe = w.np;
+    if (pb >= pe) return;
+    const long ld = w.ld;
     const int ro = left ? 0 : 1;                // first nonzero row of reflector j is j + ro
-    double *w = (double *)workspace;
-    double *V = w;   w += (size_t)ld * npad;
-    double *VT = w;  w += (size_t)ld * npad;
-    double *G = w;   w += (size_t)np * NBW * NBW;
-    double *T = w;   w += (size_t)np * NBW * NBW;
-    double *W = w;   w += (size_t)NBW * nc;
-    double *Wp = w;
-
+    const int j0 = pb * NBW, ncols = (pe - pb) * NBW, nbatch = pe - pb;
+    double *Vp = w.V + (size_t)j0 * ld;
     if (left) {
-        extract_left_kernel<<<ceil_div(ld * npad, 256), 256, 0, st>>>(rows, nref, npad, A, lda, V, ld);
+        extract_left_kernel<<<ceil_div(ld * ncols, 256), 256, 0, st>>>(rows, nref, j0, ncols, A, lda, Vp, ld);
     } else {
-        dim3 grid(ceil_div(ld, 32), ceil_div(npad, 32));
-        extract_right_kernel<<<grid, 256, 0, st>>>(rows, nref, npad, A, lda, V, ld);
+        dim3 grid(ceil_div(ld, 32), ceil_div(ncols, 32));
+        extract_right_kernel<<<grid, 256, 0, st>>>(rows, nref, j0, ncols, A, lda, Vp, ld);
     }
     SVD_KERNEL_CHECK();
-
-    // Gram matrices of all panels in one batched launch: G_p = V_p^T V_p, K = rows - p0 - ro
+    // Gram matrices of the panels in one batched launch: G_p = V_p^T V_p, K = rows - p0 - ro.  The long K is
+    // split (partials in the panels' own VT columns, which are written last) so that the launch is wide and
+    // short: it may run on a low-priority stream next to the factorization and must not hold SMs for long.
+    const long sP = (long)NBW * (ld + 1);       // panel p starts NBW rows and NBW columns further
     {
+        const int Kmax = rows - ro - j0;
+        int gs = Kmax / 512;
+        if (gs > 16) gs = 16;
+        if (gs > (int)(ld / NBW)) gs = (int)(ld / NBW);
+        if (gs < 1) gs = 1;
         GemmArgs g = {};
-        g.M = NBW; g.N = NBW; g.K = rows - ro;
-        g.A = V + ro; g.lda = ld; g.transA = 1;
-        g.B = V + ro; g.ldb = ld; g.transB = 0;
-        g.C = G; g.ldc = NBW; g.alpha = 1.0; g.beta = 0.0;
-        g.batch = np; g.sA = (long)NBW * (ld + 1); g.sB = g.sA; g.sC = (long)NBW * NBW; g.dK = NBW;
-        g.splitk = 1;
-        dgemm_dmma(g, st);
+        g.M = NBW; g.N = NBW; g.K = Kmax;
+        g.A = w.V + ro + pb * sP; g.lda = ld; g.transA = 1;
+        g.B = g.A; g.ldb = ld; g.transB = 0;
+        g.alpha = 1.0; g.beta = 0.0;
+        g.batch = nbatch; g.sA = sP; g.sB = sP; g.sC = (long)NBW * NBW; g.dK = NBW;
+        double *Gp = w.G + (size_t)pb * NBW * NBW;
+        if (gs > 1) {
+            double *part = w.VT + (size_t)j0 * ld;              // >= gs * nbatch * NBW^2 doubles
+            g.C = part; g.ldc = NBW; g.splitk = gs; g.sSplit = (long)nbatch * NBW * NBW;
+            dgemm_dmma(g, st);
+            sum_partials(Gp, NBW, part, NBW, g.sSplit, gs, NBW, NBW * nbatch, 1.0, 0.0, st);
+        } else {
+            g.C = Gp; g.ldc = NBW; g.splitk = 1;
+            dgemm_dmma(g, st);
+        }
     }
     {
         const int smem = NBW * (NBW + 1) * (int)sizeof(double);
         SVD_CUDA_CHECK(cudaFuncSetAttribute(wy_tinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        wy_tinv_kernel<<<np, NBW, smem, st>>>(G, T);
+        wy_tinv_kernel<<<nbatch, NBW, smem, st>>>(w.G + (size_t)pb * NBW * NBW, w.T + (size_t)pb * NBW * NBW);
     }
     SVD_KERNEL_CHECK();
-    // VT_p = V_p T_p for all panels: (rows - p0 - ro) x NBW
+    // VT_p = V_p T_p: (rows - p0 - ro) x NBW
     {
-        SVD_CUDA_CHECK(cudaMemsetAsync(VT, 0, sizeof(double) * (size_t)ld * npad, st));
+        SVD_CUDA_CHECK(cudaMemsetAsync(w.VT + (size_t)j0 * ld, 0, sizeof(double) * (size_t)ld * ncols, st));
         GemmArgs g = {};
-        g.M = rows - ro; g.N = NBW; g.K = NBW;
-        g.A = V + ro; g.lda = ld; g.transA = 0;
-        g.B = T; g.ldb = NBW; g.transB = 0;
-        g.C = VT + ro; g.ldc = ld; g.alpha = 1.0; g.beta = 0.0;
-        g.batch = np; g.sA = (long)NBW * (ld + 1); g.sB = (long)NBW * NBW; g.sC = g.sA; g.dM = NBW;
+        g.M = rows - ro - j0; g.N = NBW; g.K = NBW;
+        g.A = w.V + ro + pb * sP; g.lda = ld; g.transA = 0;
+        g.B = w.T + (size_t)pb * NBW * NBW; g.ldb = NBW; g.transB = 0;
+        g.C = w.VT + ro + pb * sP; g.ldc = ld; g.alpha = 1.0; g.beta = 0.0;
+        g.batch = nbatch; g.sA = sP; g.sB = (long)NBW * NBW; g.sC = sP; g.dM = NBW;
         g.splitk = 1;
         dgemm_dmma(g, st);
     }
+}
+
+// C (rows x nc, ldc) <- H_0 H_1 ... H_{nref-1} C from prepared panels (only V and VT are read):
+// panels last to first,  W = V_p^T C[p0+ro:, :] ;  C[p0+ro:, :] -= VT_p W
+void wy_apply_prepared(int left, int rows, int nref, const void *panels, double *C, long ldc, int nc,
+                       void *workspace, cudaStream_t st)
+{
+    if (nref <= 0 || nc <= 0) return;
+    const WyPanels w = wy_carve(const_cast<void *>(panels), rows, nref);
+    const long ld = w.ld;
+    const int ro = left ? 0 : 1;
+    double *W = (double *)workspace;
+    double *Wp = W + (size_t)NBW * nc;
     int dev = 0, nsm = 148;
     SVD_CUDA_CHECK(cudaGetDevice(&dev));
     SVD_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-    // panels last to first:  W = V_p^T C[p0+ro:, :] ;  C[p0+ro:, :] -= VT_p W
-    for (int p = np - 1; p >= 0; --p) {
+    for (int p = w.np - 1; p >= 0; --p) {
         const int r0 = p * NBW + ro;
         const int K = rows - r0;
         if (K <= 0) continue;
-        const double *Vp = V + r0 + (long)p * NBW * ld;
-        const double *VTp = VT + r0 + (long)p * NBW * ld;
+        const double *Vp = w.V + r0 + (long)p * NBW * ld;
+        const double *VTp = w.VT + r0 + (long)p * NBW * ld;
         const int split = pick_split(ceil_div(nc, 64) * ceil_div(NBW, 128), K, nsm);
         GemmArgs g1 = {};
         g1.M = NBW; g1.N = nc; g1.K = K;
@@ -200,6 +254,16 @@ void wy_apply_device(int left, int rows, int nref, const double *A, long lda, do
         g2.C = C + r0; g2.ldc = ldc; g2.alpha = -1.0; g2.beta = 1.0; g2.batch = 1; g2.splitk = 1;
         dgemm_dmma(g2, st);
     }
+}
+
+// set-up + apply in one call (phase-level entry points, QR-first U = Q [U_R; 0])
+void wy_apply_device(int left, int rows, int nref, const double *A, long lda, double *C, long ldc, int nc,
+                     void *workspace, cudaStream_t st)
+{
+    if (nref <= 0 || nc <= 0) return;
+    char *apply_ws = (char *)workspace + wy_panels_bytes(rows, nref);
+    wy_setup_device(left, rows, nref, A, lda, workspace, 0, wy_panel_count(nref), st);
+    wy_apply_prepared(left, rows, nref, workspace, C, ldc, nc, apply_ws, st);
 }
 
 
@@ -373,7 +437,8 @@ size_t qr_workspace_bytes(int m, int n)
 
 // A (m x n, m >= n) <- reflectors (from the diagonal down) and, above the diagonal, R's strict upper
 // triangle; R (n x n, ldr) receives the full triangular factor.
-void qr_device(int m, int n, double *A, long lda, double *R, long ldr, void *workspace, cudaStream_t st)
+void qr_device(int m, int n, double *A, long lda, double *R, long ldr, void *workspace, cudaStream_t st,
+               const ProgressHook *hook)
 {
     const long ldv = round_up(m, 2);
     double *w = (double *)workspace;
@@ -421,6 +486,8 @@ void qr_device(int m, int n, double *A, long lda, double *R, long ldr, void *wor
             }
         }
         const int ntrail = n - p0 - pw;
+        // the panel's reflectors are final (the trailing update below only touches later columns)
+        if (hook && hook->fn) hook->fn(hook->user, p0 + pw, st);
         if (ntrail <= 0) break;
         // ---- trailing update  A2 <- A2 - (V T^T) (V^T A2),  T = (striu(V^T V) + I/2)^-1
         const int rows = m - p0;

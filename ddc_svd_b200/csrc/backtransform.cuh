@@ -14,5 +14,22 @@ void wy_apply_device(int left, int rows, int nref, const double *A, long lda, do
 // overwritten with the reflectors (diagonal and below) and R's strict upper triangle, R (n x n)
 // receives the triangular factor; wy_apply_device(left = 1, rows = m, nref = n, A, ...) applies Q.
 size_t qr_workspace_bytes(int m, int n);
-void qr_device(int m, int n, double *A, long lda, double *R, long ldr, void *workspace, cudaStream_t st);
+struct ProgressHook;
+void qr_device(int m, int n, double *A, long lda, double *R, long ldr, void *workspace, cudaStream_t st,
+               const ProgressHook *hook = nullptr);
+// The same back-transform in two halves, so that the panel set-up (which depends on the reflectors only)
+// can run while the factorization is still producing the later reflectors, on another stream, and so
+// that other devices can be handed the prepared panels instead of the reflector matrix:
+//   wy_setup_device      panels [pb, pe) of NBW reflectors: gather, Gram, T, VT = V T  -> `panels`
+//   wy_apply_prepared    C <- H_0 ... H_{nref-1} C reading only V and VT of `panels`
+//   wy_panel_slices      the V / VT column ranges of panels [pb, pe) (contiguous: what gets broadcast)
+int wy_panel_width();
+int wy_panel_count(int nref);
+size_t wy_panels_bytes(int rows, int nref);
+size_t wy_apply_workspace_bytes(int nc);
+void wy_setup_device(int left, int rows, int nref, const double *A, long lda, void *panels, int pb, int pe,
+                     cudaStream_t st);
+void wy_apply_prepared(int left, int rows, int nref, const void *panels, double *C, long ldc, int nc,
+                       void *workspace, cudaStream_t st);
+void wy_panel_slices(void *panels, int rows, int nref, int pb, int pe, double **V, double **VT, size_t *count);
 }

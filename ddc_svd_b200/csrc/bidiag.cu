@@ -836,7 +836,7 @@ static void fused_set_attributes()
 // ---- on-chip tail (bidiag_tail.cuh): from step i on, if the trailing block fits the SMs' shared memory
 static int g_tail_ctas = -1;            // co-resident CTAs of the tail kernel (0: not available)
 static bool g_tail2_ok = false;
-static int g_tail_mode = 1;             // SVD_GPU_TAIL: 1 = kernel version 1 (default), 2 = experimental version 2
+static int g_tail_mode = 2;             // SVD_GPU_TAIL: 2 = kernel version 2 (default), 1 = version 1 (kept for cross-checks)
 // does the trailing block of step i fit the shared memory of `ctas` CTAs (columns dealt round-robin)?
 static bool tail_fits_ctas(int m, int n, int i, int ctas)
 {
@@ -845,6 +845,9 @@ static bool tail_fits_ctas(int m, int n, int i, int ctas)
     if (L0 > TL_MAXROWS || R0 < 1) return false;
     const long Lp = round_up(L0, 2);
     const int cpc = ceil_div(R0, ctas);
+    // one warp per owned row below the pivot, and the last warp never owns one (it polls RR / R1): with fewer
+    // co-resident CTAs than a full B200 (MIG slice, cut-down part) tall blocks must stay on the streaming path
+    if (L0 > 1 && ceil_div(L0 - 1, ctas) > TL_WARPS - 1) return false;
     return cpc <= TL_CPC && (long)cpc * Lp <= TL_CAP;
 }
 static bool tail_fits(int m, int n, int i) { return tail_fits_ctas(m, n, i, g_tail_ctas); }
@@ -912,7 +915,7 @@ static void launch_tail(int m, int n, int i, double *A, long lda, double *alpha,
 }
 
 void bidiag_device(int m, int n, double *A, long lda, double *alpha, double *beta, void *workspace,
-                   int nb, cudaStream_t st)
+                   int nb, cudaStream_t st, const ProgressHook *hook)
 {
     if (nb <= 0 || nb > NBMAX) nb = 32;
     const int mn = (m < n) ? m : n;
@@ -936,7 +939,7 @@ void bidiag_device(int m, int n, double *A, long lda, double *alpha, double *bet
     // SVD_GPU_TAIL=0/1: finish on chip once the trailing block fits into shared memory (bidiag_tail.cuh)
     const char *tenv = getenv("SVD_GPU_TAIL");
     const bool use_tail = tenv ? (tenv[0] != '0') : (TAIL_DEFAULT_ON != 0);
-    g_tail_mode = (tenv && tenv[0] == '2') ? 2 : 1;
+    g_tail_mode = (tenv && tenv[0] == '1') ? 1 : 2;
     if (use_tail) tail_init();
     bool dots1_ready = false;       // dots1p holds dots1_parts partial dot vectors of the current column c
     int dots1_parts = 0;
@@ -968,6 +971,8 @@ void bidiag_device(int m, int n, double *A, long lda, double *alpha, double *bet
             launch_tail(m, n, i, A, lda, alpha, beta, b, st);
             break;
         }
+        // reflectors [0, i) are final (column j and row j are last written by step j)
+        if (hook && hook->fn && i > 0 && hook->every > 0 && i % hook->every == 0) hook->fn(hook->user, i, st);
         if (k == 0) {
             const int nb_next = (m - i >= nb_big_min && n - i >= nb_big_min) ? nb_big : nb_small;
             // the dot slots finish_xf left for this step are laid out for the previous panel's width
@@ -1077,6 +1082,7 @@ void bidiag_device(int m, int n, double *A, long lda, double *alpha, double *bet
             k = 0;
         }
     }
+    if (hook && hook->fn) hook->fn(hook->user, mn, st);
 }
 
 // One streaming pass over the full matrix (step 0, empty panel), for roofline measurements.

@@ -48,17 +48,21 @@ struct TailArgs {
 };
 constexpr size_t TL_WS_SLOTS = (size_t)TL_MAXG * TL_MAXROWS + 3 * TL_MAXROWS + 2 * TL_MAXG + 8;
 
+// Both halves travel as 64-bit elements of one 16-byte vector access: the PTX memory model makes every
+// naturally aligned element of a vector access single-copy atomic, so {lo, tag} and {hi, tag} can each
+// only be seen whole (as 32-bit elements a torn {lo, tag} pair would be legal, if unseen on this hardware).
 __device__ __forceinline__ void tl_put(TlSlot *s, double v, unsigned tag)
 {
-    asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %2};" ::"l"(s), "r"((unsigned)__double2loint(v)),
-                 "r"(tag), "r"((unsigned)__double2hiint(v)) : "memory");
+    const unsigned long long a = (unsigned long long)(unsigned)__double2loint(v) | ((unsigned long long)tag << 32);
+    const unsigned long long b = (unsigned long long)(unsigned)__double2hiint(v) | ((unsigned long long)tag << 32);
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(s), "l"(a), "l"(b) : "memory");
 }
 __device__ __forceinline__ bool tl_try(const TlSlot *s, unsigned tag, double &v)
 {
-    unsigned lo, t0, hi, t1;
-    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(t0), "=r"(hi), "=r"(t1) : "l"(s) : "memory");
-    v = __hiloint2double((int)hi, (int)lo);
-    return t0 == tag && t1 == tag;
+    unsigned long long a, b;
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(s) : "memory");
+    v = __hiloint2double((int)(unsigned)b, (int)(unsigned)a);
+    return (unsigned)(a >> 32) == tag && (unsigned)(b >> 32) == tag;
 }
 // a poll that lasts seconds is a protocol bug: trap instead of hanging the device
 struct TlWatch {

@@ -22,6 +22,9 @@
 #include "ddc.cuh"
 #include <vector>
 #include <algorithm>
+#include <map>
+#include <mutex>
+#include <utility>
 
 namespace svdgpu {
 
@@ -483,9 +486,25 @@ size_t ddc_workspace_bytes(int N)
     return (size_t)N * (per_pos + per_node + 40 * sizeof(int)) + (64 << 10);
 }
 
-void ddc_values_device(int N, const double *b1, const double *b2, double *sigma, void *workspace,
-                       cudaStream_t st)
+// The merge tree depends on N only: its tables (node offsets / sizes / children by level, position -> node
+// per level) are built once per (device, N) and kept on the device, so that a call neither copies from
+// pageable host memory nor synchronises the stream (the reference recurses on the host instead,
+// Calculations-Parallel.c:731-766).
+struct DdcTables {
+    int nn = 0, nlev = 0;
+    std::vector<int> lvl_first;
+    int *d_tab = nullptr;            // off | N | K | c1 | c2 (nn each) | pos2node (nlev x N)
+};
+static std::map<std::pair<int, int>, DdcTables> g_ddc_tables;
+static std::mutex g_ddc_mu;
+
+static const DdcTables &ddc_tables(int N)
 {
+    int dev = 0;
+    SVD_CUDA_CHECK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_ddc_mu);
+    auto it = g_ddc_tables.find({dev, N});
+    if (it != g_ddc_tables.end()) return it->second;
     // ---- tree (sizes only; the recursion of Calculations-Parallel.c:731-766 unrolled)
     std::vector<HNode> nodes;
     nodes.reserve((size_t)N + 8);
@@ -498,7 +517,8 @@ void ddc_values_device(int N, const double *b1, const double *b2, double *sigma,
     std::stable_sort(order.begin(), order.end(),
                      [&](int a, int b) { return nodes[a].level < nodes[b].level; });
     for (int i = 0; i < nn; ++i) newid[order[i]] = i;
-    std::vector<int> h_off(nn), h_N(nn), h_K(nn), h_c1(nn), h_c2(nn), lvl_first(nlev + 1, 0);
+    std::vector<int> tab((size_t)5 * nn + (size_t)nlev * N, -1), lvl_first(nlev + 1, 0);
+    int *h_off = tab.data(), *h_N = h_off + nn, *h_K = h_N + nn, *h_c1 = h_K + nn, *h_c2 = h_c1 + nn, *h_p2n = h_c2 + nn;
     for (int i = 0; i < nn; ++i) {
         const HNode &nd = nodes[order[i]];
         h_off[i] = nd.off; h_N[i] = nd.N; h_K[i] = nd.K;
@@ -507,10 +527,28 @@ void ddc_values_device(int N, const double *b1, const double *b2, double *sigma,
         lvl_first[nd.level + 1]++;
     }
     for (int l = 0; l < nlev; ++l) lvl_first[l + 1] += lvl_first[l];
-    std::vector<int> h_p2n((size_t)nlev * N, -1);
     for (int l = 1; l < nlev; ++l)
         for (int i = lvl_first[l]; i < lvl_first[l + 1]; ++i)
             for (int t = 0; t < h_N[i]; ++t) h_p2n[(size_t)l * N + h_off[i] + t] = i - lvl_first[l];
+    DdcTables T;
+    T.nn = nn; T.nlev = nlev; T.lvl_first = lvl_first;
+    SVD_CUDA_CHECK(cudaMalloc(&T.d_tab, sizeof(int) * tab.size()));
+    SVD_CUDA_CHECK(cudaMemcpy(T.d_tab, tab.data(), sizeof(int) * tab.size(), cudaMemcpyHostToDevice));
+    // a handful of sizes per process in practice; keep the cache from growing without bound
+    if (g_ddc_tables.size() >= 64) {
+        for (auto &kv : g_ddc_tables) cudaFree(kv.second.d_tab);
+        (void)cudaGetLastError();
+        g_ddc_tables.clear();
+    }
+    return g_ddc_tables.emplace(std::make_pair(dev, N), std::move(T)).first->second;
+}
+
+void ddc_values_device(int N, const double *b1, const double *b2, double *sigma, void *workspace,
+                       cudaStream_t st)
+{
+    const DdcTables &T = ddc_tables(N);
+    const int nn = T.nn, nlev = T.nlev;
+    const std::vector<int> &lvl_first = T.lvl_first;
 
     // ---- carve the workspace
     char *w = (char *)workspace;
@@ -525,23 +563,12 @@ void ddc_values_device(int N, const double *b1, const double *b2, double *sigma,
     D.c0 = (double *)take(sizeof(double) * nn);  D.s0 = (double *)take(sizeof(double) * nn);
     D.zsum = (double *)take(sizeof(double) * nn);
     D.nact = (int *)take(sizeof(int) * nn);
-    int *d_off = (int *)take(sizeof(int) * nn), *d_N = (int *)take(sizeof(int) * nn);
-    int *d_K = (int *)take(sizeof(int) * nn), *d_c1 = (int *)take(sizeof(int) * nn);
-    int *d_c2 = (int *)take(sizeof(int) * nn);
-    int *d_p2n = (int *)take(sizeof(int) * (size_t)nlev * N);
+    int *d_off = T.d_tab, *d_N = d_off + nn, *d_K = d_N + nn, *d_c1 = d_K + nn, *d_c2 = d_c1 + nn;
+    int *d_p2n = d_c2 + nn;
     D.n_off = d_off; D.n_N = d_N; D.n_K = d_K; D.n_c1 = d_c1; D.n_c2 = d_c2;
     if ((size_t)(w - (char *)workspace) > ddc_workspace_bytes(N)) {
         fprintf(stderr, "ddc_values_device: workspace too small\n"); abort();
     }
-    // pageable -> device copies are staged by the runtime before returning, so the host
-    // vectors may go out of scope afterwards
-    SVD_CUDA_CHECK(cudaMemcpyAsync(d_off, h_off.data(), sizeof(int) * nn, cudaMemcpyHostToDevice, st));
-    SVD_CUDA_CHECK(cudaMemcpyAsync(d_N, h_N.data(), sizeof(int) * nn, cudaMemcpyHostToDevice, st));
-    SVD_CUDA_CHECK(cudaMemcpyAsync(d_K, h_K.data(), sizeof(int) * nn, cudaMemcpyHostToDevice, st));
-    SVD_CUDA_CHECK(cudaMemcpyAsync(d_c1, h_c1.data(), sizeof(int) * nn, cudaMemcpyHostToDevice, st));
-    SVD_CUDA_CHECK(cudaMemcpyAsync(d_c2, h_c2.data(), sizeof(int) * nn, cudaMemcpyHostToDevice, st));
-    SVD_CUDA_CHECK(cudaMemcpyAsync(d_p2n, h_p2n.data(), sizeof(int) * (size_t)nlev * N,
-                                   cudaMemcpyHostToDevice, st));
 
     // ---- level 0: all leaves at once
     {
@@ -569,8 +596,6 @@ void ddc_values_device(int N, const double *b1, const double *b2, double *sigma,
         SVD_KERNEL_CHECK();
     }
     SVD_CUDA_CHECK(cudaMemcpyAsync(sigma, D.sig, sizeof(double) * (size_t)N, cudaMemcpyDeviceToDevice, st));
-    // the tree tables above were copied from pageable host vectors that die at return
-    SVD_CUDA_CHECK(cudaStreamSynchronize(st));
 }
 
 } // namespace svdgpu

@@ -6,7 +6,7 @@ namespace svdgpu {
 // Singular values (ascending) of the N x (N+1) upper bidiagonal with diagonal b1[N] and
 // super-diagonal b2[N] (b2[N-1] = 0 for a square B) — the contract of the reference's
 // GetSingularValues_Parallel (Calculations-Parallel.c:852-874).  Device pointers.
-// Synchronises `st` before returning (host-built tree tables are staged per call).
+// Only enqueues on `st` (the merge-tree tables are cached on the device per N).
 size_t ddc_workspace_bytes(int N);
 void ddc_values_device(int N, const double *b1, const double *b2, double *sigma, void *workspace,
                        cudaStream_t st);

@@ -221,7 +221,7 @@ template <bool TA, bool TB> static void launch_t(const GemmArgs &g, cudaStream_t
 int dgemm_ws_mode()
 {
     const char *e = getenv("SVD_GPU_GEMM_WS");
-    return e ? atoi(e) : DGEMM_WS_DEFAULT;      // 0: off, 1: 128 x 64 tiles, one CTA per SM, 2: 64 x 64 tiles, two per SM
+    return e ? atoi(e) : DGEMM_WS_DEFAULT;      // 0: one-tile-per-CTA kernel, otherwise the persistent one
 }
 bool dgemm_ws_enabled() { return dgemm_ws_mode() != 0; }
 

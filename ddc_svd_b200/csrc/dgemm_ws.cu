@@ -24,9 +24,9 @@ namespace svdgpu {
 namespace {
 
 constexpr int WS_BN = 64, WS_BK = 16;
-// BM = 128: one 384-thread CTA per SM (8 consumer + 4 producer warps), the default.
-// BM = 64 (SVD_GPU_GEMM_WS=2, experiment): two 192-thread CTAs per SM (4 + 2 warps) on 64 x 64 tiles, so that
-// one CTA's C-tile load / epilogue overlaps the other's DMMAs (short-K updates), at 33 % more operand traffic.
+// BM = 128: one 384-thread CTA per SM (8 consumer + 4 producer warps).  A BM = 64 instantiation (two
+// 192-thread CTAs per SM on 64 x 64 tiles) was measured slower in round 1 (8192^2 back-transform 84 -> 92 ms,
+// profiles/r01_exp10_ws_64x64_two_ctas.log) and validated-then-removed in round 2; the template keeps the parameter.
 
 // HASC: the accumulators start from a staged C tile (updates): 4 stages + the C buffer.  Pure products
 // (W = V^T C streams its B operand from HBM) get 6 stages and no C buffer instead.
@@ -399,11 +399,7 @@ template <int BM, bool TA, bool TB, bool HASC> void launch_ws_c(const GemmArgs &
 template <bool TA, bool TB> void launch_ws(const GemmArgs &g, cudaStream_t st)
 {
     const bool hasc = (g.splitk <= 1 && g.beta != 0.0);
-    if (dgemm_ws_mode() == 2) {
-        if (hasc) launch_ws_c<64, TA, TB, true>(g, st); else launch_ws_c<64, TA, TB, false>(g, st);
-    } else {
-        if (hasc) launch_ws_c<128, TA, TB, true>(g, st); else launch_ws_c<128, TA, TB, false>(g, st);
-    }
+    if (hasc) launch_ws_c<128, TA, TB, true>(g, st); else launch_ws_c<128, TA, TB, false>(g, st);
 }
 
 } // namespace

@@ -70,8 +70,7 @@ def test_bidiag_vs_golden_reference(D, name):
 @pytest.mark.parametrize("shape", [(1, 1), (2, 2), (3, 3), (5, 4), (33, 33), (64, 64), (200, 200), (513, 512),
                                    (300, 200), (97, 3), (40, 1), (1500, 1400), (2040, 1100), (2100, 2000),
                                    (2500, 2500)])
-# SVD_GPU_TAIL=2 (kernel version 2) is an experiment that is not the default: SVD_TEST_EXPERIMENTAL=1 adds it
-@pytest.mark.parametrize("tail", ["1"] + (["2"] if os.environ.get("SVD_TEST_EXPERIMENTAL") else []))
+@pytest.mark.parametrize("tail", ["1", "2"])       # version 2 is the default since round 2, version 1 stays as a cross-check
 def test_bidiag_on_chip_tail(D, shape, tail, monkeypatch):
     # bidiag_tail.cuh: once the trailing block fits the SMs' shared memory the rest of the factorization runs
     # in one cooperative launch (small inputs entirely, larger ones from the first panel boundary that fits)
@@ -379,8 +378,7 @@ def test_svd_gpu_vs_oracle_512(D):
                                   (0, 1, 1000, 900, 64), (0, 0, 700, 513, 128), (0, 1, 256, 256, 16),
                                   (0, 0, 1531, 777, 100), (0, 1, 4100, 300, 64)])
 @pytest.mark.parametrize("alpha_beta", [(-1.0, 1.0), (1.0, 1.0), (0.5, 0.0), (0.5, 2.0)])
-# ws = 2 (64 x 64 tiles, two CTAs per SM) is an experiment that is not the default: SVD_TEST_EXPERIMENTAL=1 adds it
-@pytest.mark.parametrize("ws", ["0", "1"] + (["2"] if os.environ.get("SVD_TEST_EXPERIMENTAL") else []))
+@pytest.mark.parametrize("ws", ["0", "1"])
 def test_dgemm_vs_numpy(D, case, alpha_beta, ws, monkeypatch):
     # (transA, transB, M, N, K).  ws = 1: updates (alpha = +-1, beta != 0) and pure products with M > 64
     # go to the persistent warp-specialised kernel (dgemm_ws.cu), everything else - and everything
@@ -431,8 +429,6 @@ def test_svd_gpu_gemm_kernels_agree(D, shape, monkeypatch):
         assert np.all(np.abs(np.sum(V0[:, sep] * V1[:, sep], axis=0)) >= 1 - 1e-8)
 
 
-@pytest.mark.skipif(not os.environ.get("SVD_TEST_EXPERIMENTAL"),
-                    reason="written without a GPU at hand: enable with SVD_TEST_EXPERIMENTAL=1, un-gate once it has run")
 @pytest.mark.parametrize("shape,world", [((900, 900), 3), ((1200, 700), 2), ((2304, 2304), 4)])
 def test_sharded_entry_points_on_one_gpu(D, shape, world):
     # SURVEY 8e on a single device: svd_gpu_values_dev (what rank 0 runs), then svd_gpu_vectors_dev once per

@@ -20,7 +20,7 @@ def _declared_symbols():
     for h in sorted(os.listdir(INC)):
         txt = open(os.path.join(INC, h)).read()
         txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-        for m in re.finditer(r"^\s*(?:const\s+)?(?:void|int|float|double|size_t|char|unsigned long long)\s*\*?\s*\*?\s*(\w+)\s*\(", txt, re.M):
+        for m in re.finditer(r"^\s*(?:const\s+)?(?:void|int|float|double|size_t|char|unsigned long long|svdgpu_group)\s*\*?\s*\*?\s*(\w+)\s*\(", txt, re.M):
             names.add(m.group(1))
     return names
 
@@ -128,7 +128,12 @@ def test_on_chip_tail_planning():
     assert f(16384, 16384, 32, 148) == 16384 - L                        # same trailing size for any square input
     assert f(200, 300, 32, 148) == 200                                  # wide inputs never (they arrive transposed)
     assert f(65536, 4096, 32, 148) == 4096                              # too tall: 61k rows never fit
-    assert f(4096, 4096, 32, 8) == 4096 - 128                           # fewer CTAs: 8 x 16 columns at most
+    # fewer CTAs (MIG slice, cut-down part): 8 x 16 columns would fit at 128 trailing rows, but a CTA has only
+    # 15 row-owning warps, so ceil(127 / 8) = 16 rows per CTA do not: the hand-over waits for 96 rows
+    assert f(4096, 4096, 32, 8) == 4096 - 96
+    for ctas in (8, 16, 37, 64, 100, 132, 148):
+        i0 = f(4096, 4096, 32, ctas)
+        assert i0 == 4096 or -(-(4096 - i0 - 1) // ctas) <= 15
 
 
 @pytest.mark.parametrize("shape,i0,G", [((1, 1), 0, 3), ((3, 3), 0, 5), ((30, 28), 0, 5), ((60, 60), 0, 7),
