@@ -52,6 +52,7 @@ SIGNATURES = [
                                    c_void_pp, c_long, c_void_pp]),
     ("svd_gpu_sharded", None, [c_void_p, c_int, c_int, c_double_p, c_double_p, c_void_pp, c_void_pp]),
     ("svd_gpu_group_phase_ms", None, [c_void_p, c_int, c_float_p]),
+    ("svdgpu_fill_rand", None, [c_double_p, c_size_t, c_double, c_double, ctypes.c_uint]),
     ("svd_gpu_check", None, [c_int, c_int, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
     ("svd_gpu_check_dev", None, [c_int, c_int, c_void_p, c_long, c_void_p, c_void_p, c_long, c_void_p, c_long,
                                  c_int, c_double_p, c_void_p]),

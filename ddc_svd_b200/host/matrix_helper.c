@@ -5,6 +5,7 @@
  * and an l2_norm_mat that the reference never defined.  Column-major throughout. */
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include "../../include/matrix_helper.h"
 
@@ -72,4 +73,12 @@ double l2_norm_mat(int m, int n, const double *A)
     double acc = 0;
     for (size_t k = 0; k < (size_t)m * n; ++k) acc += A[k] * A[k];
     return sqrt(acc);
+}
+
+/* The input recipe of the reference's drivers (test-whole-svd.c:18-24,69-73: rand_d(1,4) in fill order with
+ * glibc's default seed 1; bidiag_dr.c:54-60,77 uses [1,2) after srand(4)): A[i] = lo + (hi-lo) * rand()/(RAND_MAX+1). */
+void svdgpu_fill_rand(double *A, size_t count, double lo, double hi, unsigned seed)
+{
+    srand(seed);
+    for (size_t i = 0; i < count; ++i) A[i] = lo + (hi - lo) * (rand() / (RAND_MAX + 1.0));
 }

@@ -90,7 +90,7 @@ static void opts_init(void)
         g_opt.qr_ratio10 = env_int("SVD_GPU_QR_RATIO10", 25);
         g_opt.wide_transpose = env_int("SVD_GPU_WIDE_TRANSPOSE", 1);
         g_opt.wy_overlap = env_int("SVD_GPU_WY_OVERLAP", 0);
-        g_opt.host_register = env_int("SVD_GPU_HOST_REGISTER", 1);
+        g_opt.host_register = env_int("SVD_GPU_HOST_REGISTER", 0);
         g_opt.ngpus = env_int("SVD_GPU_NGPUS", 1);
         g_opt.inited = 1;
     }
@@ -802,8 +802,10 @@ void svd_gpu_sharded(svdgpu_group *g, int m, int n, double *A, double *sigma, do
         }
         free(pl);
     }
-    /* page-lock the caller's buffers for the call: the reference's callers pass malloc'd memory
-     * (test-whole-svd.c:44-66), and a pageable copy neither overlaps nor reaches the link rate */
+    /* The reference's callers pass malloc'd memory (test-whole-svd.c:44-66).  Page-locking it for the call
+     * ("host_register") is optional and OFF by default: measured on a B200 box (bench.py e2e_pageable),
+     * cudaHostRegister + unregister cost more than the pageable copies lose — 16384^2: 4.55 s registered vs
+     * 3.77 s plain (3.57 s with buffers the caller page-locked once); 4096^2: 0.277 vs 0.121 (0.108). */
     int regA = 1, regU[SVD_MAX_DEV], regV[SVD_MAX_DEV];
     const double t_h2d0 = wall_ms();
     for (int lr = 0; lr < g->nlocal; ++lr) { regU[lr] = regV[lr] = 1; }

@@ -41,7 +41,7 @@ void svd_gpu_last_phase_ms(float ms[7]);
 /* tunables (also read once from the environment: SVD_GPU_NB, SVD_GPU_RQI, SVD_GPU_DEVICE, SVD_GPU_QR_FIRST,
  * SVD_GPU_WIDE_TRANSPOSE, SVD_GPU_NGPUS, SVD_GPU_HOST_REGISTER, SVD_GPU_WY_OVERLAP):
  * "nb", "rqi", "qr_first", "qr_ratio10", "wide_transpose", "ngpus" (GPUs svd_gpu() uses), "host_register"
- * (page-lock the caller's buffers for the call), "wy_overlap" (prepare WY panels during the factorization
+ * (page-lock the caller's malloc'd buffers for the call; off by default: measured slower than pageable copies), "wy_overlap" (prepare WY panels during the factorization
  * even on one GPU), "release". */
 void svd_gpu_set_option(const char *name, int value);
 
@@ -104,6 +104,11 @@ void svd_gpu_check(int m, int n, const double *A0, const double *sigma, const do
                    double out6[6]);
 void svd_gpu_check_dev(int m, int n, const double *dA0, long lda, const double *dsigma, const double *dU,
                        long ldu, const double *dV, long ldv, int nc, double out6[6], void *stream);
+
+/* the reference drivers' input recipe (test-whole-svd.c:18-24,69-73; bidiag_dr.c:54-60,77): uniform [lo,hi)
+ * from glibc rand() after srand(seed), in fill order — bench.py and the self-checking driver feed exactly the
+ * matrices the reference's own drivers would */
+void svdgpu_fill_rand(double *A, size_t count, double lo, double hi, unsigned seed);
 
 #ifdef __cplusplus
 }

@@ -123,7 +123,7 @@ def test_pageable_and_page_locked_callers_agree(D):
         D.set_option("host_register", 1)
         s1, U1, V1, A1 = D.svd_gpu(A)
     finally:
-        D.set_option("host_register", 1)
+        D.set_option("host_register", 0)
     assert np.array_equal(s0, s1) and np.array_equal(U0, U1) and np.array_equal(V0, V1) and np.array_equal(A0, A1)
     bounds_ok(A, s1, U1, V1)
 
