@@ -150,6 +150,9 @@ SIGNATURES = [
     ("svdgpu_check_workspace", c_size_t, [c_int, c_int, c_int]),
     ("svdgpu_check", None, [c_int, c_int, c_void_p, c_long, c_void_p, c_void_p, c_long, c_void_p, c_long, c_int,
                             c_void_p, c_void_p, c_void_p]),
+    ("svdgpu_ozaki_workspace", c_size_t, [c_int, c_int]),
+    ("svdgpu_ozaki_update", None, [c_int, c_int, c_double, c_void_p, c_long, c_void_p, c_long, c_void_p, c_long,
+                                   c_void_p, c_void_p]),
     ("svdgpu_dgemm", None, [c_int, c_int, c_int, c_int, c_int, c_double, c_void_p, c_long, c_void_p, c_long,
                             c_double, c_void_p, c_long, c_void_p]),
     ("svdgpu_scale_matrix", None, [c_int, c_int, c_void_p, c_long, c_void_p, c_void_p, c_void_p]),

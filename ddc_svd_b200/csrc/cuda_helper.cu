@@ -10,6 +10,7 @@
 #include "twisted.cuh"
 #include "backtransform.cuh"
 #include "check.cuh"
+#include "ozaki.cuh"
 #include "../../include/cuda-helper.h"
 #include <cstring>
 #include <nccl.h>
@@ -251,6 +252,12 @@ void svdgpu_transpose(int m, int n, const double *dA, long lda, double *dAt, lon
 void svdgpu_scale_vector(int n, double *dx, const double *dfactor, void *stream)
 {
     scale_vector_device(n, dx, dfactor, S(stream));
+}
+size_t svdgpu_ozaki_workspace(int M, int N) { return ozaki_workspace_bytes(M, N); }
+void svdgpu_ozaki_update(int M, int N, double sign, const double *dA, long lda, const double *dB, long ldb, double *dC,
+                         long ldc, void *dwork, void *stream)
+{
+    ozaki_update_device(M, N, sign, dA, lda, dB, ldb, dC, ldc, dwork, S(stream));
 }
 size_t svdgpu_check_workspace(int m, int n, int nc) { return check_workspace_bytes(m, n, nc); }
 void svdgpu_check(int m, int n, const double *dA0, long lda, const double *dsigma, const double *dU, long ldu,

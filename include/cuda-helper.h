@@ -129,6 +129,13 @@ void   svdgpu_qr_progress(int m, int n, double *dA, long lda, double *dR, long l
 void   svdgpu_dgemm(int transA, int transB, int M, int N, int K, double alpha, const double *dA,
                     long lda, const double *dB, long ldb, double beta, double *dC, long ldc,
                     void *stream);
+/* The same update C += sign * A (M x 128) * B (128 x N) on the 5th-generation tensor cores: tcgen05 has no FP64
+ * kind, so the operands are cut into 8 signed 7-bit slices (error-free), the 36 slice products with i + j <= 7
+ * run as tcgen05.mma.kind::i8 into int32 accumulators in tensor memory and are recombined in FP64 (Ozaki
+ * scheme).  K is the compact-WY panel width (128).  dwork: svdgpu_ozaki_workspace(M, N) bytes. */
+size_t svdgpu_ozaki_workspace(int M, int N);
+void   svdgpu_ozaki_update(int M, int N, double sign, const double *dA, long lda, const double *dB, long ldb,
+                           double *dC, long ldc, void *dwork, void *stream);
 /* power-of-two range guard (no counterpart in the reference, which overflows/underflows on inputs
  * near 1e+-150): dscale[0] <- factor applied to dA in place (1.0 unless max|A| is outside
  * [1e-100, 1e100]), dscale[1] <- its inverse; dwork needs 1024 doubles.  svdgpu_scale_vector

@@ -373,3 +373,40 @@ def test_sharded_one_process_per_gpu(D, shape, world, tmp_path):
     s1, U1, V1, _ = D.svd_gpu(A)
     assert np.array_equal(sig, s1)
     assert np.abs(U - U1).max() <= 1e-11 and np.abs(V - V1).max() <= 1e-11
+
+
+# ------------------------------------------------------------------ tcgen05: FP64-accurate update from int8 slice products
+@pytest.mark.parametrize("shape", [(128, 32), (128, 512), (300, 70), (1000, 513), (4100, 2050), (16384, 1024)])
+@pytest.mark.parametrize("sign", [-1.0, 1.0])
+def test_ozaki_update_vs_numpy(D, shape, sign):
+    # C += sign * A (M x 128) * B (128 x N) on the int8 tensor cores (ozaki.cu): 8 x 8 error-free slices, 36 products,
+    # int32 accumulators in TMEM, FP64 recombination — must match the FP64 product at the level of its own rounding
+    M, N = shape
+    K = 128
+    L = D.lib()
+    rng = np.random.default_rng(M + N)
+    A = np.asfortranarray(rng.standard_normal((M, K)) * np.exp(rng.uniform(-6, 0, size=(M, 1))))   # rows of very different size
+    B = np.asfortranarray(rng.standard_normal((K, N)) / 16.0)
+    C = np.asfortranarray(rng.standard_normal((M, N)))
+    bufs = []
+
+    def put(a):
+        d = L.svdgpu_malloc(a.nbytes); bufs.append(d)
+        L.svdgpu_h2d(d, util.p(a), a.nbytes, None)
+        return d
+    try:
+        dA, dB, dC = put(A), put(B), put(C)
+        work = L.svdgpu_malloc(L.svdgpu_ozaki_workspace(M, N)); bufs.append(work)
+        L.svdgpu_ozaki_update(M, N, sign, dA, M, dB, K, dC, M, work, None)
+        out = np.empty((M, N), order="F")
+        L.svdgpu_d2h(util.p(out), dC, out.nbytes, None)
+        L.svdgpu_stream_sync(None)
+    finally:
+        for d in bufs:
+            L.svdgpu_free(d)
+    ref = C + sign * (A @ B)
+    # error budget: the slices resolve 2^-56 of each operand's max-abs; FP64's own bound is K eps |A||B|
+    scale = np.abs(A).max() * np.abs(B).max()
+    err = np.abs(out - ref).max()
+    print("ozaki update", shape, "max err %.3e = %.2f eps*K*scale" % (err, err / (EPS * K * scale)))
+    assert err <= 2 * EPS * K * scale + 4 * EPS * np.abs(ref).max()
