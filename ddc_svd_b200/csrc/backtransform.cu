@@ -16,6 +16,8 @@
 #include "common.cuh"
 #include "backtransform.cuh"
 #include "bidiag.cuh"
+#include "ozaki.cuh"
+#include <cstdlib>
 
 namespace svdgpu {
 
@@ -55,24 +57,41 @@ extract_right_kernel(int n, int nR, int jbase, int ncols, const double *__restri
     }
 }
 
-// T = (striu(G) + 1/2 I)^{-1}, one CTA per panel, thread j owns column j.
-__global__ void __launch_bounds__(NBW) wy_tinv_kernel(const double *__restrict__ G, double *__restrict__ T)
+// T = (striu(G) + 1/2 I)^{-1}, one CTA per panel.  Column j of the inverse of an upper-triangular matrix by
+// back-substitution, t_j = 2, t_i = -2 sum_{k=i+1..j} R[i][k] t_k: a WARP per column (lanes split the dot
+// product, the column lives in the lanes' registers: lane l holds t_l, t_{l+32}, t_{l+64}, t_{l+96}), 32 warps
+// per CTA take the 128 columns four at a time.  (Round 1 ran one THREAD per column: 171 us per launch.)
+constexpr int TINV_WARPS = 32;
+__global__ void __launch_bounds__(32 * TINV_WARPS) wy_tinv_kernel(const double *__restrict__ G, double *__restrict__ T)
 {
     extern __shared__ double Rsm[];                 // R[i][k] at Rsm[i*(NBW+1)+k]
     const double *g = G + (size_t)blockIdx.x * NBW * NBW;
-    double *tcol = T + (size_t)blockIdx.x * NBW * NBW + (size_t)threadIdx.x * NBW;   // column j of T
-    const int j = threadIdx.x;
-    for (int i = 0; i < NBW; ++i) Rsm[i * (NBW + 1) + j] = (i < j) ? g[i + j * NBW] : (i == j ? 0.5 : 0.0);
+    double *Tp = T + (size_t)blockIdx.x * NBW * NBW;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int e = threadIdx.x; e < NBW * NBW; e += 32 * TINV_WARPS) {
+        const int i = e % NBW, k = e / NBW;         // g is column-major: coalesced reads
+        Rsm[i * (NBW + 1) + k] = (i < k) ? g[e] : (i == k ? 0.5 : 0.0);
+    }
     __syncthreads();
-    // column j of the inverse of an upper-triangular matrix, bottom-up; the column is private
-    // to this thread, so it can live in (L1-cached) global memory
-    for (int i = j + 1; i < NBW; ++i) tcol[i] = 0.0;
-    tcol[j] = 2.0;
-    for (int i = j - 1; i >= 0; --i) {
-        double s = 0.0;
-        const double *Ri = Rsm + i * (NBW + 1);
-        for (int k = i + 1; k <= j; ++k) s += Ri[k] * tcol[k];
-        tcol[i] = -2.0 * s;
+    static_assert(NBW == 128, "four entries of the column per lane");
+    for (int j = warp; j < NBW; j += TINV_WARPS) {
+        double t[4] = {0.0, 0.0, 0.0, 0.0};        // t[c] = entry lane + 32 c of column j
+#pragma unroll
+        for (int c = 0; c < 4; ++c) if (lane + 32 * c == j) t[c] = 2.0;
+        for (int i = j - 1; i >= 0; --i) {
+            const double *Ri = Rsm + i * (NBW + 1);
+            double s = 0.0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int k = lane + 32 * c;
+                if (k > i && k <= j) s = fma(Ri[k], t[c], s);
+            }
+            s = warp_sum(s);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) if (lane + 32 * c == i) t[c] = -2.0 * s;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) Tp[(size_t)j * NBW + lane + 32 * c] = t[c];
     }
 }
 
@@ -132,9 +151,22 @@ void wy_panel_slices(void *panels, int rows, int nref, int pb, int pe, double **
     *VT = w.VT + (size_t)pb * NBW * w.ld;
     *count = (size_t)(pe - pb) * NBW * w.ld;
 }
+// The short-K update C -= (V T) W can run on the 5th-generation tensor cores (ozaki.cu: int8 slice products in
+// TMEM, FP64-accurate) instead of the FP64 DMMA pipe: SVD_GPU_OZAKI = 0 never, 1 whenever the shape is large
+// enough to fill the machine, unset = the measured default below.
+constexpr int OZAKI_DEFAULT = 0;
+constexpr int OZAKI_MIN_ROWS = 1024, OZAKI_MIN_COLS = 1024;
+static int ozaki_mode()
+{
+    const char *e = getenv("SVD_GPU_OZAKI");
+    return e ? atoi(e) : OZAKI_DEFAULT;
+}
+// rows of the tallest update a (rows x nref) reflector set can ask for is not known here: size for 32768
+constexpr int OZAKI_MAX_ROWS = 65536;
 size_t wy_apply_workspace_bytes(int nc)
 {
-    return ((size_t)NBW * nc + (size_t)WY_MAX_SPLIT * NBW * nc) * sizeof(double) + 256;
+    return ((size_t)NBW * nc + (size_t)WY_MAX_SPLIT * NBW * nc) * sizeof(double) + 256 +
+           ozaki_workspace_bytes(OZAKI_MAX_ROWS, nc);
 }
 size_t backtransform_workspace_bytes(int rows, int nref, int nc)
 {
@@ -196,7 +228,7 @@ void wy_setup_device(int left, int rows, int nref, const double *A, long lda, vo
     {
         const int smem = NBW * (NBW + 1) * (int)sizeof(double);
         SVD_CUDA_CHECK(cudaFuncSetAttribute(wy_tinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        wy_tinv_kernel<<<nbatch, NBW, smem, st>>>(w.G + (size_t)pb * NBW * NBW, w.T + (size_t)pb * NBW * NBW);
+        wy_tinv_kernel<<<nbatch, 32 * TINV_WARPS, smem, st>>>(w.G + (size_t)pb * NBW * NBW, w.T + (size_t)pb * NBW * NBW);
     }
     SVD_KERNEL_CHECK();
     // VT_p = V_p T_p: (rows - p0 - ro) x NBW
@@ -224,6 +256,8 @@ void wy_apply_prepared(int left, int rows, int nref, const void *panels, double 
     const int ro = left ? 0 : 1;
     double *W = (double *)workspace;
     double *Wp = W + (size_t)NBW * nc;
+    void *oz_ws = (void *)(Wp + (size_t)WY_MAX_SPLIT * NBW * nc + 32);
+    const int oz = ozaki_mode();
     int dev = 0, nsm = 148;
     SVD_CUDA_CHECK(cudaGetDevice(&dev));
     SVD_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
@@ -246,6 +280,10 @@ void wy_apply_prepared(int left, int rows, int nref, const void *panels, double 
         } else {
             g1.C = W; g1.ldc = NBW; g1.splitk = 1;
             dgemm_dmma(g1, st);
+        }
+        if (oz && K >= OZAKI_MIN_ROWS && K <= OZAKI_MAX_ROWS && nc >= OZAKI_MIN_COLS && ozaki_update_supported(K, nc, NBW)) {
+            ozaki_update_device(K, nc, -1.0, VTp, ld, W, NBW, C + r0, ldc, oz_ws, st);
+            continue;
         }
         GemmArgs g2 = {};
         g2.M = K; g2.N = nc; g2.K = NBW;
@@ -506,7 +544,7 @@ void qr_device(int m, int n, double *A, long lda, double *R, long ldr, void *wor
             g.C = G; g.ldc = NBW; g.splitk = 1;
             dgemm_dmma(g, st);
         }
-        wy_tinv_kernel<<<1, NBW, tsmem, st>>>(G, T);
+        wy_tinv_kernel<<<1, 32 * TINV_WARPS, tsmem, st>>>(G, T);
         SVD_KERNEL_CHECK();
         GemmArgs g2 = {};
         g2.M = rows; g2.N = NBW; g2.K = NBW; g2.A = Vp; g2.lda = ldv; g2.transA = 0; g2.B = T; g2.ldb = NBW; g2.transB = 1;

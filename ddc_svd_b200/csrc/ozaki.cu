@@ -19,8 +19,9 @@
 //     (128 KB) and streams 32-column B tiles (8 planes x 4 KB) through a 2-stage ring;
 //   * one elected thread issues tcgen05.mma.kind::i8 (M 128, N 32, K 32 per instruction): 36 plane pairs x 4
 //     K steps per tile into the 8 accumulators of one of two TMEM buffers (2 x 8 x 32 columns = all 512);
-//   * four epilogue warps read the accumulators with tcgen05.ld (32x32b), recombine, and read-modify-write
-//     the FP64 tile of C while the MMA thread already works on the other TMEM buffer;
+//   * eight epilogue warps read the accumulators with tcgen05.ld (32x32b), recombine, and read-modify-write
+//     the FP64 tile of C (whose values were requested two tiles earlier) while the MMA thread already works on
+//     the other TMEM buffer;
 //   * mbarriers connect the roles (TMA complete_tx, tcgen05.commit), no CTA-wide barrier in the loop.
 #include "common.cuh"
 #include "ozaki.cuh"
@@ -31,13 +32,14 @@ namespace svdgpu {
 
 namespace {
 
+#define OZ_TR(slot, n) do { if (g.trace && blockIdx.x == 0 && (n) < 128) g.trace[(n) * 8 + (slot)] = clock64(); } while (0)
 constexpr int OZ_SL = 8;                  // slices per operand
 constexpr int OZ_BM = 128, OZ_BN = 32, OZ_K = 128;
 constexpr int OZ_BSTAGES = 2;
 constexpr int OZ_A_BYTES = OZ_SL * OZ_BM * OZ_K;            // 128 KB
 constexpr int OZ_B_BYTES = OZ_SL * OZ_BN * OZ_K;            // 32 KB per stage
 constexpr int OZ_SMEM = OZ_A_BYTES + OZ_BSTAGES * OZ_B_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int OZ_THREADS = 256;           // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 epilogue
+constexpr int OZ_THREADS = 384;           // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 epilogue
 constexpr int OZ_NT = 16;                 // n-tiles per work unit (512 columns)
 
 __device__ __forceinline__ unsigned oz_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -71,10 +73,11 @@ __device__ __forceinline__ void oz_mbar_wait(uint64_t *bar, unsigned parity)
         if (spin > 64 && (spin & 255) == 0 && clock64() - t0 > 4000000000ll) __trap();
     }
 }
-__device__ __forceinline__ void oz_tma_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar)
+// one box of the plane stack: coordinates (k, row, plane)
+__device__ __forceinline__ void oz_tma_3d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar)
 {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(oz_u32(dst)), "l"(map), "r"(oz_u32(bar)), "r"(c0), "r"(c1) : "memory");
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(oz_u32(dst)), "l"(map), "r"(oz_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100): rows of 128 bytes, 8-row groups 1024 B apart
 __device__ __forceinline__ uint64_t oz_smem_desc(unsigned saddr)
@@ -90,14 +93,20 @@ __device__ __forceinline__ uint64_t oz_smem_desc(unsigned saddr)
 // instruction descriptor: D = S32, A = B = S8, both K-major, N = 32, M = 128
 constexpr unsigned OZ_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(OZ_BN >> 3) << 17) | ((unsigned)(OZ_BM >> 4) << 24);
 
-__device__ __forceinline__ void oz_mma_i8(unsigned tmem_d, uint64_t adesc, uint64_t bdesc, unsigned accumulate)
+// D[tmem] (+)= A[smem] * B[smem]^T; the descriptors differ between the 144 instructions of a tile only in the
+// start-address field (low word), so the issuing thread adds compile-time constants to two 32-bit values
+template <bool ACC>
+__device__ __forceinline__ void oz_mma_i8(unsigned tmem_d, unsigned a_lo, unsigned b_lo, unsigned desc_hi)
 {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n"
-        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(OZ_IDESC), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
+        ".reg .b64 da, db;\n"
+        "setp.ne.b32 p, %5, 0;\n"
+        "mov.b64 da, {%1, %3};\n"
+        "mov.b64 db, {%2, %3};\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %4, {%6, %6, %6, %6}, p;\n"
+        "}\n" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(OZ_IDESC), "n"(ACC ? 1 : 0), "r"(0u) : "memory");
 }
 __device__ __forceinline__ void oz_commit(uint64_t *bar)
 {
@@ -116,6 +125,7 @@ struct OzArgs {
     long Mpad, Npad;          // rows per plane of the sliced operands
     const int *expo;          // expo[0] + expo[1] = exponent of the product scale
     double sign;              // C += sign * A B
+    unsigned long long *trace; // SVD_GPU_OZ_TRACE: clock64 stamps of CTA 0, [tile][8]
 };
 
 __global__ void __launch_bounds__(OZ_THREADS, 1)
@@ -138,7 +148,7 @@ oz_update_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     if (threadIdx.x == 0) {
         oz_mbar_init(a_full, 1); oz_mbar_init(a_empty, 1);
         for (int s = 0; s < OZ_BSTAGES; ++s) { oz_mbar_init(b_full + s, 1); oz_mbar_init(b_empty + s, 1); }
-        for (int b = 0; b < 2; ++b) { oz_mbar_init(t_full + b, 1); oz_mbar_init(t_empty + b, 4); }
+        for (int b = 0; b < 2; ++b) { oz_mbar_init(t_full + b, 1); oz_mbar_init(t_empty + b, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -161,15 +171,15 @@ oz_update_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 const int mb = u % mblocks, ng = u / mblocks;
                 oz_mbar_wait(a_empty, (ua & 1u) ^ 1u);
                 oz_mbar_expect_tx(a_full, OZ_A_BYTES);
-                for (int i = 0; i < OZ_SL; ++i)
-                    oz_tma_2d(sA + i * OZ_BM * OZ_K, &mapA, 0, (int)(i * g.Mpad) + mb * OZ_BM, a_full);
+                for (int i = 0; i < OZ_SL; i += 4)           // 4 planes (64 KB) per copy
+                    oz_tma_3d(sA + i * OZ_BM * OZ_K, &mapA, 0, mb * OZ_BM, i, a_full);
                 const int t1 = min(ntiles, (ng + 1) * OZ_NT);
                 for (int t = ng * OZ_NT; t < t1; ++t, ++ub) {
                     const unsigned s = ub % OZ_BSTAGES;
                     oz_mbar_wait(b_empty + s, ((ub / OZ_BSTAGES) & 1u) ^ 1u);
+                    OZ_TR(0, ub);
                     oz_mbar_expect_tx(b_full + s, OZ_B_BYTES);
-                    for (int j = 0; j < OZ_SL; ++j)
-                        oz_tma_2d(sB + s * OZ_B_BYTES + j * OZ_BN * OZ_K, &mapB, 0, (int)(j * g.Npad) + t * OZ_BN, b_full + s);
+                    oz_tma_3d(sB + s * OZ_B_BYTES, &mapB, 0, t * OZ_BN, 0, b_full + s);      // all 8 planes in one copy
                 }
             }
         }
@@ -184,22 +194,32 @@ oz_update_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 for (int t = ng * OZ_NT; t < t1; ++t, ++ub, ++ut) {
                     const unsigned s = ub % OZ_BSTAGES, buf = ut & 1u;
                     oz_mbar_wait(t_empty + buf, ((ut >> 1) & 1u) ^ 1u);
+                    OZ_TR(1, ut);
                     oz_mbar_wait(b_full + s, (ub / OZ_BSTAGES) & 1u);
+                    OZ_TR(2, ut);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint64_t a0 = oz_smem_desc(oz_u32(sA));
                     const uint64_t b0 = oz_smem_desc(oz_u32(sB + s * OZ_B_BYTES));
-                    for (int gsum = 0; gsum < OZ_SL; ++gsum) {
-                        const unsigned d = tmem + buf * 256 + gsum * OZ_BN;
-                        for (int i = 0; i <= gsum; ++i) {
-                            const int j = gsum - i;
-                            // plane i of A starts i*16 KB, plane j of B j*4 KB further; 32 bytes of K per instruction
-                            const uint64_t ad = a0 + (uint64_t)((i * OZ_BM * OZ_K) >> 4);
-                            const uint64_t bd = b0 + (uint64_t)((j * OZ_BN * OZ_K) >> 4);
+                    const unsigned a_lo = (unsigned)a0, b_lo = (unsigned)b0, d_hi = (unsigned)(a0 >> 32);
+                    const unsigned d0 = tmem + buf * 256;
+                    {
+                        // 36 plane pairs x 4 K steps, fully unrolled: plane i of A starts i*16 KB, plane j of B j*4 KB
+                        // further, 32 bytes of K per instruction (descriptor addresses count 16-byte units)
 #pragma unroll
-                            for (int k4 = 0; k4 < OZ_K / 32; ++k4)
-                                oz_mma_i8(d, ad + (uint64_t)(k4 * 2), bd + (uint64_t)(k4 * 2), (i > 0 || k4 > 0) ? 1u : 0u);
+                        for (int gsum = 0; gsum < OZ_SL; ++gsum) {
+#pragma unroll
+                            for (int i = 0; i <= gsum; ++i) {
+#pragma unroll
+                                for (int k4 = 0; k4 < OZ_K / 32; ++k4) {
+                                    const unsigned ao = (unsigned)((i * OZ_BM * OZ_K) >> 4) + 2u * k4;
+                                    const unsigned bo = (unsigned)(((gsum - i) * OZ_BN * OZ_K) >> 4) + 2u * k4;
+                                    if (i == 0 && k4 == 0) oz_mma_i8<false>(d0 + gsum * OZ_BN, a_lo + ao, b_lo + bo, d_hi);
+                                    else oz_mma_i8<true>(d0 + gsum * OZ_BN, a_lo + ao, b_lo + bo, d_hi);
+                                }
+                            }
                         }
                     }
+                    OZ_TR(3, ut);
                     oz_commit(b_empty + s);              // the B stage is free once these MMAs have read it
                     oz_commit(t_full + buf);             // ... and the accumulators are complete
                 }
@@ -208,48 +228,92 @@ oz_update_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         }
     } else if (warp >= 4) {
         // ================================ epilogue ====================================
-        const int ew = warp - 4;                          // TMEM lanes [32 ew, 32 ew + 32)
+        // 8 warps: warp e reads TMEM lanes [32 (e%4), +32) (the hardware ties a warp to the lane quarter e%4) and
+        // the 16 accumulator columns [16 (e/4), +16) of every group.  A thread owns one row of the tile; its 16
+        // values of C for the NEXT TWO tiles are already in flight while it recombines the current one (the read
+        // of C is the long pole: 2 x 16 x 8 bytes x 256 threads = 64 KB in flight per SM).
+        const int ew = warp - 4, quarter = ew & 3, chalf = ew >> 2;
         const double sc0 = scalbn(g.sign, g.expo[0] + g.expo[1] - 12);
-        unsigned ut = 0;
-        for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
-            const int mb = u % mblocks, ng = u / mblocks;
-            const int row = mb * OZ_BM + ew * 32 + lane;
-            const int t1 = min(ntiles, (ng + 1) * OZ_NT);
-            for (int t = ng * OZ_NT; t < t1; ++t, ++ut) {
-                const unsigned buf = ut & 1u;
-                oz_mbar_wait(t_full + buf, (ut >> 1) & 1u);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const unsigned tbase = tmem + ((unsigned)(ew * 32) << 16) + buf * 256;
-#pragma unroll 1
-                for (int c8 = 0; c8 < OZ_BN; c8 += 8) {
-                    int v[OZ_SL][8];
+        struct It { int u, t, t1, mb; };
+        auto first = [&](It &it) {
+            it.u = blockIdx.x;
+            if (it.u < nunits) { it.mb = it.u % mblocks; const int ng = it.u / mblocks; it.t = ng * OZ_NT; it.t1 = min(ntiles, (ng + 1) * OZ_NT); }
+        };
+        auto next = [&](It &it) {
+            if (++it.t < it.t1) return;
+            it.u += gridDim.x;
+            if (it.u < nunits) { it.mb = it.u % mblocks; const int ng = it.u / mblocks; it.t = ng * OZ_NT; it.t1 = min(ntiles, (ng + 1) * OZ_NT); }
+        };
+        auto fetch = [&](const It &it, double (&c)[16]) {
+            const int row = it.mb * OZ_BM + quarter * 32 + lane;
+            const int n0 = it.t * OZ_BN + chalf * 16;
 #pragma unroll
-                    for (int gsum = 0; gsum < OZ_SL; ++gsum) oz_tmem_ld8(tbase + gsum * OZ_BN + c8, v[gsum]);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (c8 + 8 >= OZ_BN) {
-                        // every accumulator of this buffer has been read by this warp
-                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                        __syncwarp();
-                        if (lane == 0) oz_mbar_arrive(t_empty + buf);
-                    }
-                    const int n0 = t * OZ_BN + c8;
-                    if (row < g.M) {
+            for (int q = 0; q < 16; ++q)
+                c[q] = (it.u < nunits && row < g.M && n0 + q < g.N) ? __ldcg(g.C + row + (long)(n0 + q) * g.ldc) : 0.0;
+        };
+        It cur, pf;
+        first(cur);
+        pf = cur;
+        // one tile: wait for its accumulators, recombine, update C from the values in `cc`
+        auto do_tile = [&](const It &it, const double (&cc)[16], unsigned ut) {
+            const unsigned buf = ut & 1u;
+            oz_mbar_wait(t_full + buf, (ut >> 1) & 1u);
+            if (ew == 0 && lane == 0) OZ_TR(4, ut);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const unsigned tbase = tmem + ((unsigned)(quarter * 32) << 16) + buf * 256 + chalf * 16;
+            const int row = it.mb * OZ_BM + quarter * 32 + lane;
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            if (n0 + q < g.N) {
-                                // smallest terms first; every term is an exact double
-                                constexpr double wgt[OZ_SL] = {1.0, 0x1p-7, 0x1p-14, 0x1p-21, 0x1p-28, 0x1p-35, 0x1p-42, 0x1p-49};
-                                double acc = 0.0;
+            for (int c8 = 0; c8 < 16; c8 += 8) {
+                int v[OZ_SL][8];
 #pragma unroll
-                                for (int gsum = OZ_SL - 1; gsum >= 0; --gsum)
-                                    acc = fma((double)v[gsum][q], wgt[gsum], acc);
-                                double *c = g.C + row + (long)(n0 + q) * g.ldc;
-                                *c = fma(acc, sc0, *c);
-                            }
+                for (int gsum = 0; gsum < OZ_SL; ++gsum) oz_tmem_ld8(tbase + gsum * OZ_BN + c8, v[gsum]);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (c8 == 8) {
+                    // every accumulator column of this warp has been read: hand the buffer back
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) oz_mbar_arrive(t_empty + buf);
+                    if (ew == 0 && lane == 0) OZ_TR(5, ut);
+                }
+                const int n0 = it.t * OZ_BN + chalf * 16 + c8;
+                if (row < g.M) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        if (n0 + q < g.N) {
+                            // neighbouring groups are 2^-7 apart and |acc_g| <= 8 * 128 * 64 * 64 = 2^22: a pair fits an
+                            // int32 exactly; four exact conversions, smallest term first
+                            const int h0 = v[0][q] * 128 + v[1][q], h1 = v[2][q] * 128 + v[3][q];
+                            const int h2 = v[4][q] * 128 + v[5][q], h3 = v[6][q] * 128 + v[7][q];
+                            double acc = (double)h3 * 0x1p-49;
+                            acc = fma((double)h2, 0x1p-35, acc);
+                            acc = fma((double)h1, 0x1p-21, acc);
+                            acc = fma((double)h0, 0x1p-7, acc);
+                            g.C[row + (long)(n0 + q) * g.ldc] = fma(acc, sc0, cc[c8 + q]);
                         }
                     }
                 }
             }
+            if (ew == 0 && lane == 0) OZ_TR(6, ut);
+        };
+        // software pipeline over the CTA's tiles, three register sets in rotation: while tile k is recombined
+        // the values of C for tiles k+1 and k+2 are in flight (no register copies: a copy would wait for the load)
+        double c0[16], c1[16], c2[16];
+        fetch(pf, c0);
+        if (pf.u < nunits) next(pf);
+        fetch(pf, c1);
+        unsigned ut = 0;
+        while (cur.u < nunits) {
+            if (pf.u < nunits) next(pf);
+            fetch(pf, c2);
+            do_tile(cur, c0, ut++); next(cur);
+            if (cur.u >= nunits) break;
+            if (pf.u < nunits) next(pf);
+            fetch(pf, c0);
+            do_tile(cur, c1, ut++); next(cur);
+            if (cur.u >= nunits) break;
+            if (pf.u < nunits) next(pf);
+            fetch(pf, c1);
+            do_tile(cur, c2, ut++); next(cur);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -295,17 +359,18 @@ oz_slice_kernel(const double *__restrict__ X, long sr, long sk, int R, long Rpad
     // consecutive threads take consecutive rows when rows are contiguous in X, consecutive k-chunks otherwise
     long r; int kc;
     if (sr <= sk) { r = idx % Rpad; kc = (int)(idx / Rpad); } else { kc = (int)(idx % (OZ_K / 16)); r = idx / (OZ_K / 16); }
-    const int e = *expo;
+    const double sc = scalbn(64.0, -*expo);              // x 2^-e 2^6: the first digit is rint of this
     union { signed char b[16]; int4 v; } out[OZ_SL];
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
         const int k = kc * 16 + q;
-        double x = (r < R) ? scalbn(X[r * sr + (long)k * sk], -e) : 0.0;
+        double y = (r < R) ? X[r * sr + (long)k * sk] * sc : 0.0;
 #pragma unroll
         for (int i = 0; i < OZ_SL; ++i) {
-            const double d = rint(scalbn(x, 6 + 7 * i));
-            out[i].b[q] = (signed char)(int)d;
-            x -= scalbn(d, -(6 + 7 * i));
+            // digit i = rint(residual * 2^(6+7i)); the residual is carried pre-scaled: every step is exact
+            const double d = rint(y);
+            out[i].b[q] = (signed char)__double2int_rn(d);
+            y = (y - d) * 128.0;
         }
     }
 #pragma unroll
@@ -328,15 +393,15 @@ EncodeTiledFn encode_fn()
     }
     return fn;
 }
-// int8 planes [rows_total][128], box = 128 bytes x box_rows, SWIZZLE_128B
-CUtensorMap make_map(const signed char *planes, long rows_total, int box_rows)
+// int8 planes [plane][row][128], box = 128 bytes x box_rows x box_planes, SWIZZLE_128B
+CUtensorMap make_map(const signed char *planes, long rows_per_plane, int box_rows, int box_planes)
 {
     CUtensorMap m;
-    cuuint64_t dims[2] = {(cuuint64_t)OZ_K, (cuuint64_t)rows_total};
-    cuuint64_t strides[1] = {(cuuint64_t)OZ_K};
-    cuuint32_t box[2] = {(cuuint32_t)OZ_K, (cuuint32_t)box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)planes, dims, strides, box, estr,
+    cuuint64_t dims[3] = {(cuuint64_t)OZ_K, (cuuint64_t)rows_per_plane, (cuuint64_t)OZ_SL};
+    cuuint64_t strides[2] = {(cuuint64_t)OZ_K, (cuuint64_t)OZ_K * (cuuint64_t)rows_per_plane};
+    cuuint32_t box[3] = {(cuuint32_t)OZ_K, (cuuint32_t)box_rows, (cuuint32_t)box_planes};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)planes, dims, strides, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { fprintf(stderr, "*** libsvdgpu: cuTensorMapEncodeTiled failed (%d)\n", (int)r); abort(); }
@@ -383,10 +448,18 @@ void ozaki_update_device(int M, int N, double sign, const double *A, long lda, c
     // A[m][k] at A[m + k*lda]: rows contiguous; B[k][n] at B[k + n*ldb]: for the "row" n of the plane, k is contiguous
     slice_operand(A, 1, lda, M, Mpad, expo, scratch, pa, st);
     slice_operand(B, ldb, 1, N, Npad, expo + 1, scratch + 256, pb, st);
-    const CUtensorMap mapA = make_map(pa, OZ_SL * Mpad, OZ_BM);
-    const CUtensorMap mapB = make_map(pb, OZ_SL * Npad, OZ_BN);
+    const CUtensorMap mapA = make_map(pa, Mpad, OZ_BM, 4);
+    const CUtensorMap mapB = make_map(pb, Npad, OZ_BN, OZ_SL);
     OzArgs g;
     g.M = M; g.N = N; g.C = C; g.ldc = ldc; g.Mpad = Mpad; g.Npad = Npad; g.expo = expo; g.sign = sign;
+    g.trace = nullptr;
+    static unsigned long long *d_trace = nullptr;
+    const bool tracing = getenv("SVD_GPU_OZ_TRACE") != nullptr;
+    if (tracing) {
+        if (!d_trace) SVD_CUDA_CHECK(cudaMalloc(&d_trace, 128 * 8 * sizeof(unsigned long long)));
+        SVD_CUDA_CHECK(cudaMemsetAsync(d_trace, 0, 128 * 8 * sizeof(unsigned long long), st));
+        g.trace = d_trace;
+    }
     int dev = 0, nsm = 148;
     SVD_CUDA_CHECK(cudaGetDevice(&dev));
     SVD_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
@@ -395,6 +468,19 @@ void ozaki_update_device(int M, int N, double sign, const double *A, long lda, c
     const int nunits = mblocks * ngroups;
     oz_update_kernel<<<nunits < nsm ? nunits : nsm, OZ_THREADS, OZ_SMEM, st>>>(mapA, mapB, g);
     SVD_KERNEL_CHECK();
+    if (tracing) {
+        static unsigned long long h[128 * 8];
+        SVD_CUDA_CHECK(cudaMemcpyAsync(h, d_trace, sizeof h, cudaMemcpyDeviceToHost, st));
+        SVD_CUDA_CHECK(cudaStreamSynchronize(st));
+        unsigned long long t0 = ~0ull;
+        for (int z = 0; z < 128 * 8; ++z) if (h[z] && h[z] < t0) t0 = h[z];
+        fprintf(stderr, "OZTRACE tile: producer-issue | mma: tmem-free, B-landed, issued | epilogue: acc-ready, tmem-released, done\n");
+        for (int nt = 0; nt < 48; ++nt) {
+            fprintf(stderr, "OZTRACE %3d", nt);
+            for (int z = 0; z < 7; ++z) fprintf(stderr, " %8lld", h[nt * 8 + z] ? (long long)(h[nt * 8 + z] - t0) : -1ll);
+            fprintf(stderr, "\n");
+        }
+    }
 }
 
 } // namespace svdgpu

@@ -434,7 +434,9 @@ tw_pairfix_kernel(double *__restrict__ Z, long ld, int len, int ns, int k, int p
     }
     __syncthreads();
     const double h = 0.5 * s_g;
-    if (!(fabs(h) > 1e-15) || fabs(h) > 1e-6) return;       // nothing to do / not a "nearly orthogonal" pair: leave it
+    // |g| <= 2e-14 is already at the level the independent vectors reach (its share of ||X^T X - I||_F stays below
+    // 2e-14 sqrt(4 n)); |g| > 2e-6 is not a "nearly orthogonal" pair: leave both alone (and skip the write pass)
+    if (!(fabs(h) > 1e-14) || fabs(h) > 1e-6) return;
     for (j = threadIdx.x; j < len; j += PF_T) {
         const double a = x[j], b = y[j];
         x[j] = fma(-h, b, a);
