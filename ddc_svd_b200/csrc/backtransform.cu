@@ -227,7 +227,9 @@ void wy_setup_device(int left, int rows, int nref, const double *A, long lda, vo
     }
     {
         const int smem = NBW * (NBW + 1) * (int)sizeof(double);
-        SVD_CUDA_CHECK(cudaFuncSetAttribute(wy_tinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        static DeviceOnce once;
+        if (first_on_device(once))
+            SVD_CUDA_CHECK(cudaFuncSetAttribute(wy_tinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         wy_tinv_kernel<<<nbatch, 32 * TINV_WARPS, smem, st>>>(w.G + (size_t)pb * NBW * NBW, w.T + (size_t)pb * NBW * NBW);
     }
     SVD_KERNEL_CHECK();
@@ -258,9 +260,12 @@ void wy_apply_prepared(int left, int rows, int nref, const void *panels, double 
     double *Wp = W + (size_t)NBW * nc;
     void *oz_ws = (void *)(Wp + (size_t)WY_MAX_SPLIT * NBW * nc + 32);
     const int oz = ozaki_mode();
-    int dev = 0, nsm = 148;
-    SVD_CUDA_CHECK(cudaGetDevice(&dev));
-    SVD_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    static int nsm = 0;
+    if (nsm == 0) {
+        int dev = 0;
+        SVD_CUDA_CHECK(cudaGetDevice(&dev));
+        SVD_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    }
     for (int p = w.np - 1; p >= 0; --p) {
         const int r0 = p * NBW + ro;
         const int K = rows - r0;

@@ -815,9 +815,8 @@ template <int RPT> static void query_clusters_t(int ri)
 }
 static void fused_set_attributes()
 {
-    static bool done = false;
-    if (done) return;
-    done = true;
+    static DeviceOnce once;
+    if (!first_on_device(once)) return;
     SVD_CUDA_CHECK(cudaFuncSetAttribute(fused_pass_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FZ_SMEM_BYTES));
     SVD_CUDA_CHECK(cudaFuncSetAttribute(fused_pass_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FZ_SMEM_BYTES));
     SVD_CUDA_CHECK(cudaFuncSetAttribute(fused_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FZ_SMEM_BYTES));
@@ -864,7 +863,9 @@ int bidiag_tail_start(int m, int n, int nb, int ctas)
 }
 static void tail_init()
 {
-    if (g_tail_ctas >= 0) return;
+    // (function attributes are per device; the co-resident CTA count is the same on every device of a box)
+    static DeviceOnce once;
+    if (!first_on_device(once)) return;
     g_tail_ctas = 0;
     int dev = 0, nsm = 0, coop = 0, per_sm = 0;
     SVD_CUDA_CHECK(cudaGetDevice(&dev));

@@ -22,6 +22,19 @@
 extern unsigned long long g_svdgpu_launches;
 #define SVD_KERNEL_CHECK() do { ++g_svdgpu_launches; SVD_CUDA_CHECK(cudaGetLastError()); } while (0)
 
+// true the first time it is called for the current device with this flag set (function attributes such as the
+// dynamic shared-memory limit are per device; setting them on every launch costs host time on the launch path)
+struct DeviceOnce { bool done[64] = {}; };
+static inline bool first_on_device(DeviceOnce &f)
+{
+    int dev = 0;
+    SVD_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return true;
+    if (f.done[dev]) return false;
+    f.done[dev] = true;
+    return true;
+}
+
 static inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 static inline long round_up(long a, long b) { return (a + b - 1) / b * b; }
 

@@ -198,10 +198,11 @@ template <int BM, int BN, bool TA, bool TB>
 static void launch_cfg(const GemmArgs &g, cudaStream_t st)
 {
     using Cfg = TileCfg<BM, BN, TA, TB>;
-    // per-device attribute; cheap enough to set on every launch (multi-GPU safe)
-    SVD_CUDA_CHECK(cudaFuncSetAttribute(dgemm_dmma_kernel<BM, BN, TA, TB>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        Cfg::SMEM_BYTES));
+    static DeviceOnce once;
+    if (first_on_device(once))
+        SVD_CUDA_CHECK(cudaFuncSetAttribute(dgemm_dmma_kernel<BM, BN, TA, TB>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            Cfg::SMEM_BYTES));
     dim3 grid(ceil_div(g.M, BM), ceil_div(g.N, BN), g.batch * g.splitk);
     dgemm_dmma_kernel<BM, BN, TA, TB><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(g);
     SVD_KERNEL_CHECK();

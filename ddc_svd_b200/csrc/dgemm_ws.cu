@@ -382,12 +382,14 @@ template <int BM, bool TA, bool TB, bool HASC> void launch_ws_c(const GemmArgs &
 {
     using Cfg = WsCfg<BM, TA, TB, HASC>;
     static int nsm = 0;
-    int dev = 0;
-    SVD_CUDA_CHECK(cudaGetDevice(&dev));
-    if (nsm == 0) SVD_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-    // per-device attribute; cheap enough to set on every launch (multi-GPU safe)
-    SVD_CUDA_CHECK(cudaFuncSetAttribute(dgemm_ws_kernel<BM, TA, TB, HASC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)Cfg::SMEM_BYTES));
+    static DeviceOnce once;
+    if (first_on_device(once)) {
+        int dev = 0;
+        SVD_CUDA_CHECK(cudaGetDevice(&dev));
+        if (nsm == 0) SVD_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+        SVD_CUDA_CHECK(cudaFuncSetAttribute(dgemm_ws_kernel<BM, TA, TB, HASC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)Cfg::SMEM_BYTES));
+    }
     const int tilesM = ceil_div(g.M, BM), tilesN = ceil_div(g.N, WS_BN);
     const int ntiles = tilesM * tilesN, nunits = ntiles * g.splitk;
     const int slots = nsm * Cfg::CTAS_PER_SM;

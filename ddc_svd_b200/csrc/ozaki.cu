@@ -463,7 +463,9 @@ void ozaki_update_device(int M, int N, double sign, const double *A, long lda, c
     int dev = 0, nsm = 148;
     SVD_CUDA_CHECK(cudaGetDevice(&dev));
     SVD_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-    SVD_CUDA_CHECK(cudaFuncSetAttribute(oz_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
+    static DeviceOnce once;
+    if (first_on_device(once))
+        SVD_CUDA_CHECK(cudaFuncSetAttribute(oz_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
     const int mblocks = (int)(Mpad / OZ_BM), ngroups = ceil_div(ceil_div(N, OZ_BN), OZ_NT);
     const int nunits = mblocks * ngroups;
     oz_update_kernel<<<nunits < nsm ? nunits : nsm, OZ_THREADS, OZ_SMEM, st>>>(mapA, mapB, g);

@@ -500,7 +500,9 @@ void twisted_vectors_device(int n, int mb, const double *a, const double *b, con
     double *sgn = w;     w += cmax + 8;
     int *kidx = (int *)w;
 
-    SVD_CUDA_CHECK(cudaFuncSetAttribute(tw_solve_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TSC_TILE_BYTES));
+    static DeviceOnce once;
+    if (first_on_device(once))
+        SVD_CUDA_CHECK(cudaFuncSetAttribute(tw_solve_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TSC_TILE_BYTES));
 
     tw_prep_kernel<<<1, 1024, 0, st>>>(n, mb, a, b, q, e, ab, pivmin);
     SVD_KERNEL_CHECK();
