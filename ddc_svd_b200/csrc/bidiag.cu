@@ -23,6 +23,7 @@
 // 4 launches per step (reference: 10-12), no host synchronisation inside the loop.
 #include "common.cuh"
 #include "bidiag.cuh"
+#include <vector>
 
 namespace svdgpu {
 
@@ -758,7 +759,17 @@ static FusedPlan plan_fused(int i, int m, int n, int mpad, int nsm, int min_rows
     return p;
 }
 
-static bool g_pdl = true;       // SVD_GPU_PDL=0 turns programmatic dependent launch off
+// Programmatic dependent launch between the fused pass and finish_xf.  g_pdl_mode (SVD_GPU_PDL): 0 never,
+// 1 (default) only for steps whose pass runs single-CTA "clusters" (trailing rows <= 4096), 2 always.  Measured
+// on a B200 (profiles/r02_bidiag_pdl.log): the early launch wins ~4 us per step where it applies (4096^2: 89.6 ->
+// 81.7 ms), but with real clusters (CS >= 2, placed inside one GPC) the early finish_xf CTAs fragment the SMs
+// the next pass's clusters need and part of them runs as a second wave: 16384^2 2.78 s with PDL everywhere,
+// 2.55 s without it.
+static int g_pdl_mode = 1;
+static int g_pdl_cs = 2;        // largest cluster size whose pass is launched as a programmatic dependent (SVD_GPU_PDL_CS)
+static int g_pdl_fin = 1;       // finish_xf as a programmatic dependent of a clustered pass (SVD_GPU_PDL_FIN)
+static bool g_pdl = true;       // the decision for the pass launch of the current step
+static bool g_pdl_f = true;     // ... and for its finish_xf
 template <int RPT> static void launch_fused_t(const FusedArgs &fa, const FusedPlan &pl, cudaStream_t st)
 {
     cudaLaunchConfig_t cfg = {};
@@ -786,7 +797,7 @@ template <int RB, typename... Args> static void launch_finish_xf(int grid, cudaS
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = g_pdl ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = g_pdl_f ? 1 : 0;
     SVD_CUDA_CHECK(cudaLaunchKernelEx(&cfg, finish_xf_kernel<RB>, args...));
 }
 static void launch_fused(const FusedArgs &fa, const FusedPlan &pl, cudaStream_t st)
@@ -915,9 +926,40 @@ static void launch_tail(int m, int n, int i, double *A, long lda, double *alpha,
     SVD_KERNEL_CHECK();
 }
 
+// SVD_GPU_BIDIAG_PROFILE=1: CUDA events around every launch of the three streaming kernel classes (fused pass,
+// finish_xf, panel GEMM), summed per class and per quarter of the factorization at the end (synchronises; run it
+// with SVD_GPU_PDL=0 so that the classes do not overlap).  A measuring aid, off by default.
+struct BdProf {
+    bool on = false;
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> cls, step;
+    void begin(int c, int i, cudaStream_t st) {
+        if (!on) return;
+        cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+        cudaEventRecord(a, st); ev.push_back(a); ev.push_back(b); cls.push_back(c); step.push_back(i);
+    }
+    void end(cudaStream_t st) { if (on) cudaEventRecord(ev.back(), st); }
+    void report(int mn, cudaStream_t st) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        double tot[3][4] = {}; int cnt[3][4] = {};
+        for (size_t k = 0; k < cls.size(); ++k) {
+            float ms = 0.f; cudaEventElapsedTime(&ms, ev[2 * k], ev[2 * k + 1]);
+            const int q = (int)((long)step[k] * 4 / (mn > 0 ? mn : 1)); tot[cls[k]][q < 4 ? q : 3] += ms; cnt[cls[k]][q < 4 ? q : 3]++;
+            cudaEventDestroy(ev[2 * k]); cudaEventDestroy(ev[2 * k + 1]);
+        }
+        const char *nm[3] = {"fused_pass", "finish_xf", "panel_gemm"};
+        for (int c = 0; c < 3; ++c)
+            fprintf(stderr, "BDPROF %-10s by quarter of the steps: %8.2f %8.2f %8.2f %8.2f ms  (launches %d %d %d %d)\n", nm[c],
+                    tot[c][0], tot[c][1], tot[c][2], tot[c][3], cnt[c][0], cnt[c][1], cnt[c][2], cnt[c][3]);
+    }
+};
+
 void bidiag_device(int m, int n, double *A, long lda, double *alpha, double *beta, void *workspace,
                    int nb, cudaStream_t st, const ProgressHook *hook)
 {
+    BdProf prof;
+    prof.on = getenv("SVD_GPU_BIDIAG_PROFILE") != nullptr;
     if (nb <= 0 || nb > NBMAX) nb = 32;
     const int mn = (m < n) ? m : n;
     const int mpad = (int)round_up(m, 2);
@@ -932,7 +974,9 @@ void bidiag_device(int m, int n, double *A, long lda, double *alpha, double *bet
     // measurement (profiles/): the split passes unless the fused pass is faster at this size
     const char *fenv = getenv("SVD_GPU_FUSED");
     const bool use_fused = (fenv != nullptr) ? (fenv[0] != '0') : FZ_DEFAULT_ON;
-    { const char *pe = getenv("SVD_GPU_PDL"); g_pdl = pe ? (pe[0] != '0') : true; }
+    { const char *pe = getenv("SVD_GPU_PDL"); g_pdl_mode = pe ? atoi(pe) : 1; g_pdl = g_pdl_f = g_pdl_mode != 0; }
+    { const char *pe = getenv("SVD_GPU_PDL_CS"); if (pe) g_pdl_cs = atoi(pe); }
+    { const char *pe = getenv("SVD_GPU_PDL_FIN"); if (pe) g_pdl_fin = atoi(pe); }
     if (use_fused) fused_set_attributes();
     // thresholds below which the split passes are used (overridable for tests)
     const char *e1 = getenv("SVD_GPU_FUSED_MIN_ROWS"), *e2 = getenv("SVD_GPU_FUSED_MIN_COLS");
@@ -988,6 +1032,8 @@ void bidiag_device(int m, int n, double *A, long lda, double *alpha, double *bet
         FusedPlan pl = {false, 1, 4, 0, 0, 0};
         if (use_fused && !tail && do_col && do_row) pl = plan_fused(i, m, n, mpad, nsm, fz_min_rows < 2 ? 2 : fz_min_rows, fz_min_cols < 1 ? 1 : fz_min_cols);
         if (pl.ok) {
+            g_pdl = (g_pdl_mode == 2) || (g_pdl_mode == 1 && pl.CS <= g_pdl_cs);
+            g_pdl_f = (g_pdl_mode == 2) || (g_pdl_mode == 1 && (pl.CS <= g_pdl_cs || g_pdl_fin));
             // ---- fused step: ONE read of the trailing matrix gives both A^T c and A r
             if (!dots1_ready) {
                 // only the panel dots / norm of c (the "extra" CTAs of gemvT, no column groups)
@@ -1011,7 +1057,9 @@ void bidiag_device(int m, int n, double *A, long lda, double *alpha, double *bet
                 SVD_CUDA_CHECK(cudaMemsetAsync(d_trace, 0, 8 * 256 * sizeof(unsigned long long), st));
                 fa.trace = d_trace;
             }
+            prof.begin(0, i, st);
             launch_fused(fa, pl, st);
+            prof.end(st);
             if (tracing) {
                 static unsigned long long h[8 * 256];
                 SVD_CUDA_CHECK(cudaMemcpyAsync(h, d_trace, sizeof h, cudaMemcpyDeviceToHost, st));
@@ -1033,6 +1081,7 @@ void bidiag_device(int m, int n, double *A, long lda, double *alpha, double *bet
                 const int rb = old_rule ? (Lb > 4096 ? 4 : 1)
                                         : (Lb <= 32 * (nsm - nColBlk)) ? 1 : (Lb <= 64 * (nsm - nColBlk)) ? 2 : 4;
                 const int nRowBlk = ceil_div(Lb, 32 * rb);
+                prof.begin(1, i, st);
                 if (rb == 1)
                     launch_finish_xf<1>(nRowBlk + nColBlk, st, A, lda, i, m, n, k, nb, b.P, b.ldp, b.Q, b.ldq, b.c,
                                         (const double *)b.rv, (const double *)b.tmpN, lda, pl.NC,
@@ -1046,6 +1095,7 @@ void bidiag_device(int m, int n, double *A, long lda, double *alpha, double *bet
                                         (const double *)b.rv, (const double *)b.tmpN, lda, pl.NC,
                                         (const double *)b.dots2p, pl.NC, beta, nRowBlk, b.dots1p);
                 dots1_parts = nRowBlk;
+                prof.end(st);
             }
             SVD_KERNEL_CHECK();
             dots1_ready = true;
@@ -1079,11 +1129,14 @@ void bidiag_device(int m, int n, double *A, long lda, double *alpha, double *bet
             g.B = b.Q + (i + 1); g.ldb = b.ldq; g.transB = 1;
             g.C = A + (i + 1) + (long)(i + 1) * lda; g.ldc = lda;
             g.alpha = -1.0; g.beta = 1.0; g.batch = 1; g.splitk = 1;
+            prof.begin(2, i, st);
             dgemm_dmma(g, st);
+            prof.end(st);
             k = 0;
         }
     }
     if (hook && hook->fn) hook->fn(hook->user, mn, st);
+    prof.report(mn, st);
 }
 
 // One streaming pass over the full matrix (step 0, empty panel), for roofline measurements.
