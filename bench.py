@@ -41,12 +41,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE captured launch of the dominant kernel
-# (ncu --set full, profiles/r01_ncu_summary_v3.md; the kernel is unchanged since): fused_pass_kernel at step
-# i=1500 of n=16384 (algorithmic single-read bytes of that launch: 8*(16384-1500)*(16384-1501) = 1.772e9)
-NCU_TRAFFIC = {16384: 1.780507e9 + 5.105664e6, 4096: 77.380864e6 + 1.881856e6}
+# (ncu --set full, round 2 capture, profiles/r02_ncu_summary.md): fused_pass_kernel at step i=1500 of n=16384
+# (algorithmic single-read bytes of that launch: 8*(16384-1500)*(16384-1501) = 1.772e9) and at step 1000 of n=4096
+NCU_TRAFFIC = {16384: 1.780506e9 + 4.453888e6, 4096: 77.3888e6 + 1.939456e6}
 NCU_TRAFFIC_NOTE = ("dram__bytes_read.sum + dram__bytes_write.sum of ONE fused_pass_kernel launch (ncu --set full): "
-                    "n=16384 step 1500 (single-read algorithmic bytes of that launch 1.772e9), "
-                    "n=4096 step 1000 (76.7e6); profiles/r01_ncu_summary_v3.md")
+                    "n=16384 step 1500 (single-read algorithmic bytes of that launch 1.772e9, 280.4 us), "
+                    "n=4096 step 1000 (76.7e6, 23.8 us); profiles/r02_ncu_summary.md")
 METRIC = "svd_gpu seconds"
 UNIT = "s"
 EPS = float(np.finfo(np.float64).eps)
