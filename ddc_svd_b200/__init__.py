@@ -48,6 +48,7 @@ SIGNATURES = [
     ("svdgpu_group_rank", c_int, [c_void_p, c_int]),
     ("svdgpu_group_device", c_int, [c_void_p, c_int]),
     ("svdgpu_shard_range", None, [c_int, c_int, c_int, c_int_p, c_int_p, c_int_p]),
+    ("svdgpu_plan_chunks", c_int, [c_int, c_int, c_int, c_int_p, c_int, c_int_p, c_int_p, c_int_p, c_int_p]),
     ("svd_gpu_sharded_dev", None, [c_void_p, c_int, c_int, c_void_p, c_long, c_void_pp, c_void_pp, c_long,
                                    c_void_pp, c_long, c_void_pp]),
     ("svd_gpu_sharded", None, [c_void_p, c_int, c_int, c_double_p, c_double_p, c_void_pp, c_void_pp]),

@@ -81,9 +81,6 @@ static void opts_init(void)
     pthread_once(&g_once, init_once);
     pthread_mutex_lock(&g_mu);
     if (!g_opt.inited) {
-        (void)svdgpu_device_count();                 /* aborts loudly when there is no GPU */
-        const char *e = getenv("SVD_GPU_DEVICE");
-        if (e) svdgpu_set_device(atoi(e));
         g_opt.nb = env_int("SVD_GPU_NB", 32);
         g_opt.rqi = env_int("SVD_GPU_RQI", 1);
         g_opt.qr_first = env_int("SVD_GPU_QR_FIRST", 1);
@@ -98,6 +95,19 @@ static void opts_init(void)
 }
 
 /* lock and return the context of device `dev` (made current) */
+static void device_init(void)
+{
+    static int done = 0;
+    pthread_mutex_lock(&g_mu);
+    if (!done) {
+        (void)svdgpu_device_count();                 /* aborts loudly when there is no GPU: there is no CPU fallback */
+        const char *e = getenv("SVD_GPU_DEVICE");
+        if (e) svdgpu_set_device(atoi(e));
+        done = 1;
+    }
+    pthread_mutex_unlock(&g_mu);
+}
+
 static svd_ctx *ctx_acquire(int dev)
 {
     opts_init();
@@ -202,6 +212,7 @@ struct svdgpu_group {
 svdgpu_group *svdgpu_group_create_local(int ndev, const int *devices)
 {
     opts_init();
+    device_init();
     if (ndev < 1 || ndev > SVD_MAX_DEV || ndev > svdgpu_device_count()) {
         fprintf(stderr, "svdgpu_group_create_local: %d devices requested, %d visible\n", ndev, svdgpu_device_count());
         abort();
@@ -220,6 +231,7 @@ svdgpu_group *svdgpu_group_create_local(int ndev, const int *devices)
 svdgpu_group *svdgpu_group_create_rank(int nranks, int rank, const void *id128)
 {
     opts_init();
+    device_init();
     svdgpu_group *g = (svdgpu_group *)calloc(1, sizeof *g);
     if (!g) abort();
     g->world = nranks; g->nlocal = 1; g->rank0 = rank;
@@ -328,6 +340,42 @@ static void plan_arena(svd_call *c, long lda)
         o += up256(w);
     }
     c->total_root = o;
+}
+
+/* Pure planning (no device): the route svd_gpu() takes for an m x n input and the canonical order in which the
+ * compact-WY panel chunks are prepared on rank 0 and broadcast — every rank derives the same list from (m, n)
+ * alone, which is what lets the other ranks post their receives before rank 0 has produced anything.
+ * route[0] = 1 if the input is solved as the SVD of its transpose, route[1] = 1 for QR first, route[2..3] = the
+ * (rows, cols) the core factorizes.  Per chunk: set (0 Q of the QR, 1 left, 2 right reflectors), first panel,
+ * end panel, and the number of reflectors of the producing factorization that must be final.  Returns the count. */
+int svdgpu_plan_chunks(int m, int n, int world, int route[4], int max_out, int *set_out, int *pb_out, int *pe_out,
+                       int *need_out)
+{
+    opts_init();
+    svdgpu_group g;
+    memset(&g, 0, sizeof g);
+    g.world = world < 1 ? 1 : world; g.nlocal = 1;
+    svd_call *c = (svd_call *)malloc(sizeof *c);
+    if (!c) abort();
+    const int wide = use_wide_transpose(m, n);
+    const int tm = wide ? n : m, tn = wide ? m : n;
+    memset(c, 0, sizeof *c);
+    c->grp = &g; c->m = tm; c->n = tn; c->mn = tm < tn ? tm : tn; c->world = g.world;
+    c->qr = use_qr_first(tm, tn);
+    plan_sets(c, NULL, 0);
+    if (route) { route[0] = wide; route[1] = c->qr; route[2] = tm; route[3] = tn; }
+    const int nbw = 128;
+    int cnt = 0;
+    for (int i = 0; i < c->norder; ++i, ++cnt) {
+        if (cnt >= max_out) continue;
+        const refl_set *s = &c->set[c->order[i][0]];
+        const int ch = c->order[i][1];
+        const int pb = ch * CHUNK_PANELS, pe = (pb + CHUNK_PANELS < s->np) ? pb + CHUNK_PANELS : s->np;
+        set_out[cnt] = c->order[i][0]; pb_out[cnt] = pb; pe_out[cnt] = pe;
+        need_out[cnt] = pe * nbw < s->nref ? pe * nbw : s->nref;
+    }
+    free(c);
+    return cnt;
 }
 
 /* ---- broadcast of one chunk of prepared panels over the local ranks (V, then V T) ----------------- */
@@ -698,6 +746,7 @@ void svd_gpu_dev(int m, int n, double *dA, long lda, double *dsigma, double *dU,
                  void *stream)
 {
     opts_init();
+    device_init();
     svdgpu_group g;
     memset(&g, 0, sizeof g);
     g.world = g.nlocal = 1; g.rank0 = 0; g.dev[0] = svdgpu_get_device();
@@ -719,6 +768,7 @@ void svd_gpu_sharded_dev(svdgpu_group *g, int m, int n, double *dA_root, long ld
 void svd_gpu_values_dev(int m, int n, double *dA, long lda, double *dalpha, double *dbeta, double *dsigma,
                         void *stream)
 {
+    device_init();
     svd_ctx *c = ctx_acquire(svdgpu_get_device());
     const int mn = m < n ? m : n;
     char *work = arena_get(c, up256(maxz(svdgpu_bidiag_workspace(m, n, lda), svdgpu_ddc_workspace(mn))));
@@ -733,6 +783,7 @@ void svd_gpu_vectors_dev(int m, int n, const double *dA_mod, long lda, const dou
                          long ldu, double *dVblk, long ldv, double *dsig_out, void *stream)
 {
     if (ns <= 0) return;
+    device_init();
     svd_ctx *c = ctx_acquire(svdgpu_get_device());
     const int mn = m < n ? m : n, len_beta = (m >= n) ? n - 1 : m, mb = len_beta + 1;
     size_t w = svdgpu_twisted_workspace(mn, mb, ns);
@@ -788,6 +839,7 @@ void svd_gpu_sharded(svdgpu_group *g, int m, int n, double *A, double *sigma, do
         abort();
     }
     opts_init();
+    device_init();
     const double t_start = wall_ms();
     const int mn = m < n ? m : n;
     const int want_vec = (Ublk != NULL && Vblk != NULL);
@@ -930,6 +982,7 @@ void svd_gpu(int m, int n, double *A, double *sigma, double *U, double *V)
         abort();
     }
     opts_init();
+    device_init();
     const int mn = m < n ? m : n;
     const int want_vec = (U != NULL && V != NULL);
     if ((U == NULL) != (V == NULL)) {
@@ -960,6 +1013,7 @@ void svd_gpu_check_dev(int m, int n, const double *dA0, long lda, const double *
                        const double *dV, long ldv, int nc, double out6[6], void *stream)
 {
     opts_init();
+    device_init();
     void *work = svdgpu_malloc(svdgpu_check_workspace(m, n, nc) + 64);
     double *dout = (double *)work;
     svdgpu_check(m, n, dA0, lda, dsigma, dU, ldu, dV, ldv, nc, dout, (char *)work + 64, stream);
@@ -972,6 +1026,7 @@ void svd_gpu_check(int m, int n, const double *A0, const double *sigma, const do
                    double out6[6])
 {
     opts_init();
+    device_init();
     const int mn = m < n ? m : n;
     double *dA = (double *)svdgpu_malloc(sizeof(double) * ((size_t)m * n + (size_t)m * mn + (size_t)n * mn + mn));
     double *dU = dA + (size_t)m * n, *dV = dU + (size_t)m * mn, *ds = dV + (size_t)n * mn;

@@ -1,4 +1,9 @@
-"""Host logic of the multi-GPU (one process per GPU) svd_gpu path — SURVEY.md 8e.
+"""CPU MODEL of the multi-GPU host logic — SURVEY.md 8e.  The product's multi-GPU path lives in the library
+(ddc_svd_b200/host/svd_gpu.c: groups of ranks, NCCL, compact-WY panels broadcast while the factorization runs;
+bench.py and the GPU tests call it through the C ABI).  This module restates its partitioning and its sequence of
+exchanges over torch.distributed so that the orchestration can be exercised on CPU with gloo
+(tests/test_sharding_gloo.py, the oracle standing in for the kernels); shard_range() is pinned to the library's
+svdgpu_shard_range() and svdgpu_plan_chunks() by tests/test_host_logic.py.
 
 The bidiagonalization and the dDC singular values do not shard (n dependent steps with global
 reductions): they run on rank 0.  The twisted-factorization vector solves and the back-transform

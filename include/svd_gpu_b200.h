@@ -66,6 +66,11 @@ int  svdgpu_group_nlocal(const svdgpu_group *g);
 int  svdgpu_group_rank(const svdgpu_group *g, int local);
 int  svdgpu_group_device(const svdgpu_group *g, int local);
 void svdgpu_shard_range(int mn, int world, int rank, int *blk, int *i0, int *ns);
+/* planning only (no device needed): the route of an m x n input (route[0] transpose, route[1] QR first, route[2..3]
+ * the shape the core factorizes) and the canonical order of the compact-WY panel chunks that rank 0 prepares and
+ * broadcasts — set (0 Q of the QR, 1 left, 2 right reflectors), panels [pb, pe), reflectors that must be final. */
+int  svdgpu_plan_chunks(int m, int n, int world, int route[4], int max_out, int *set_out, int *pb_out, int *pe_out,
+                        int *need_out);
 
 /* Device-resident sharded SVD.  dA_root: the matrix on rank 0's device (ignored elsewhere), overwritten
  * as by svd_gpu_dev.  Per local rank lr: dsigma[lr][min(m,n)] receives ALL singular values, dUblk[lr]

@@ -149,3 +149,63 @@ def test_on_chip_tail_model_matches_oracle(shape, i0, G):
     assert np.abs(Ag - Ao).max() <= 1e-11 and np.abs(ag - ao).max() <= 1e-11
     if n > 1:
         assert np.abs(bg - bo).max() <= 1e-11
+
+
+def test_shard_range_c_matches_python_model():
+    # svdgpu_shard_range (svd_gpu.c) is the partitioning every rank of a sharded run derives for itself; the CPU
+    # model in ddc_svd_b200/sharding.py (exercised over gloo) must be the same function
+    import ddc_svd_b200 as D
+    from ddc_svd_b200.sharding import shard_range
+    for mn in (1, 2, 3, 7, 64, 100, 129, 4096, 16384, 32768):
+        for world in (1, 2, 3, 4, 5, 8):
+            cover = []
+            for r in range(world):
+                assert D.shard_range(mn, world, r) == shard_range(mn, world, r)
+                _, i0, ns = D.shard_range(mn, world, r)
+                cover += list(range(i0, i0 + ns))
+            assert cover == list(range(mn))
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (2, 2), (5, 5), (130, 130), (4096, 4096), (16384, 16384), (5000, 4096),
+                                   (65536, 4096), (300, 900), (4096, 32768), (700, 129)])
+def test_panel_chunk_plan_is_the_same_on_every_rank(shape):
+    # svdgpu_plan_chunks: the canonical order in which rank 0 prepares / broadcasts compact-WY panel chunks.  The other
+    # ranks post their receives from this list before rank 0 has produced anything, so it must depend on (m, n) only,
+    # cover every panel of every reflector set exactly once, and never ask for a chunk before an earlier one.
+    import ctypes
+    import ddc_svd_b200 as D
+    L = D.lib()
+    m, n = shape
+    plans = []
+    for world in (1, 2, 8):
+        route = (ctypes.c_int * 4)()
+        cap = 4096
+        arr = [(ctypes.c_int * cap)() for _ in range(4)]
+        cnt = L.svdgpu_plan_chunks(m, n, world, route, cap, *arr)
+        assert 0 < cnt <= cap
+        plans.append((list(route), [tuple(a[i] for a in arr) for i in range(cnt)]))
+    assert plans[0] == plans[1] == plans[2]
+    route, chunks = plans[0]
+    wide, qr, tm, tn = route
+    assert wide == (1 if m < n else 0) and (tm, tn) == ((n, m) if m < n else (m, n))
+    assert qr == (1 if tm * 10 >= tn * 25 and tm > tn and tn >= 2 else 0)
+    nL = min(tm, tn) if not qr else tn
+    nR = (tn - 2 if tn >= 2 else 0)
+    expect = {1: nL, 2: nR}
+    if qr:
+        expect[0] = tn
+    seen = {}
+    last_need = {0: 0, 1: 0}
+    for st, pb, pe, need in chunks:
+        assert pb == seen.get(st, 0) and pe > pb            # contiguous, in order, per set
+        seen[st] = pe
+        stage = 0 if st == 0 else 1
+        assert need >= last_need[stage] or need == expect[st]   # the producing factorization only moves forward
+        last_need[stage] = max(last_need[stage], need)
+        assert need <= expect[st]
+    for st, nref in expect.items():
+        if nref > 0:
+            assert seen[st] == -(-nref // 128), (st, seen, nref)
+    if qr:      # the QR's chunks all come before the bidiagonalization's
+        first_bd = min(i for i, c in enumerate(chunks) if c[0] != 0)
+        assert all(c[0] == 0 for c in chunks[:first_bd]) and all(c[0] != 0 for c in chunks[first_bd:])
