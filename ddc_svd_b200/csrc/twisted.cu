@@ -204,7 +204,12 @@ tw_solve_scan_kernel(const TwSolveArgs a)
     const double *__restrict__ q = a.pr.q, *__restrict__ e = a.pr.e, *__restrict__ ab = a.pr.ab;
     const int Lseg = ((mb + TSC_W - 1) / TSC_W + 31) / 32 * 32;
     const int sa = min(mb, w * Lseg), sb = min(mb, sa + Lseg);   // this warp's output positions [sa, sb)
-    const int kmax = __reduce_max_sync(0xffffffffu, k), kmin = __reduce_min_sync(0xffffffffu, k);
+    int kmax = k, kmin = k;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+        kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+    }
     if (w == 0) s_k[lane] = k;
 
     // ---- sweep 1 --------------------------------------------------------------------------------
@@ -271,7 +276,7 @@ tw_solve_scan_kernel(const TwSolveArgs a)
         for (int r = 0; r < 32; ++r) {
             const int kr = s_k[r];
             const bool mine = down ? (pos < kr) : (pos >= kr);
-            if (t0 + r < ns && pos < sb && mine) {
+            if (t0 + r < ns && pos >= sa && pos < sb && mine) {
                 const long o = a.rev ? (long)(mb - 1 - pos) : (long)pos;
                 a.X[(size_t)(t0 + r) * a.ldx + o] = tl[lane * 33 + r];
             }
@@ -303,9 +308,11 @@ tw_solve_scan_kernel(const TwSolveArgs a)
         }
     }
     {   // up side (and the twist position itself, z_k = 1), blocks of 32 positions from the bottom
+        // (an empty trailing segment, sa == sb == mb, must not touch the block that holds position mb-1: it belongs
+        //  to another warp — found by compute-sanitizer timing, see tests/test_gpu_round2.py::test_twisted_every_entry_written)
         const int lo = max(sa, kmin);
         double z = cup * scale;
-        for (int jb = lo & ~31; jb < sb; jb += 32) {
+        for (int jb = lo & ~31; sa < sb && jb < sb; jb += 32) {
             const int pbot = max(jb, lo), pend = min(jb + 32, sb);
             for (int pb = pbot; pb < pend; pb += TSC_UB) {
                 double pv[TSC_UB];

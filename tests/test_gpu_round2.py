@@ -410,3 +410,44 @@ def test_ozaki_update_vs_numpy(D, shape, sign):
     err = np.abs(out - ref).max()
     print("ozaki update", shape, "max err %.3e = %.2f eps*K*scale" % (err, err / (EPS * K * scale)))
     assert err <= 2 * EPS * K * scale + 4 * EPS * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 33, 63, 65, 100, 257, 300, 511, 1000, 1025, 2049])
+def test_twisted_every_entry_written_once(D, n):
+    # svdgpu_twisted_vectors writes the normalised vectors straight into X / Y from several warps per sigma (position
+    # segments, tw_solve_scan_kernel).  Poison the outputs AND the workspace, run twice, and require (i) no poison left,
+    # (ii) bitwise identical results, (iii) orthonormal vectors: a segment that writes outside its positions (the bug
+    # compute-sanitizer's timing exposed at n = 257: an empty trailing segment overwrote position n-1) fails (ii)/(iii).
+    L = D.lib()
+    A = util.rand_matrix(max(2 * n - 1, 1), n)
+    _, al, be = util.oracle_bidiag(A)
+    B = util.bidiag_dense(al, be)
+    sv = np.ascontiguousarray(np.linalg.svd(B, compute_uv=False)[::-1])
+    bep = np.zeros(n); bep[:n - 1] = be
+    outs = []
+    for fill in (0xFF, 0x7F):
+        bufs = [L.svdgpu_malloc(8 * (3 * n + 2)), L.svdgpu_malloc(8 * n * n), L.svdgpu_malloc(8 * n * n)]
+        wb = L.svdgpu_twisted_workspace(n, n, n)
+        bufs.append(L.svdgpu_malloc(wb))
+        d, dX, dY, work = bufs
+        try:
+            L.svdgpu_memset(work, fill, wb, None)
+            L.svdgpu_memset(dX, fill, 8 * n * n, None); L.svdgpu_memset(dY, fill, 8 * n * n, None)
+            L.svdgpu_h2d(d, util.p(al), 8 * n, None); L.svdgpu_h2d(d + 8 * n, util.p(bep), 8 * n, None)
+            L.svdgpu_h2d(d + 16 * n + 8, util.p(sv), 8 * n, None)
+            L.svdgpu_twisted_vectors(n, n, d, d + 8 * n, d + 16 * n + 8, n, 0, n, dX, n, dY, n, None, 1, work, None)
+            X = np.zeros((n, n)); Y = np.zeros((n, n))
+            L.svdgpu_d2h(util.p(X), dX, 8 * n * n, None); L.svdgpu_d2h(util.p(Y), dY, 8 * n * n, None)
+            L.svdgpu_stream_sync(None)
+        finally:
+            for b in bufs:
+                L.svdgpu_free(b)
+        assert np.isfinite(X).all() and np.isfinite(Y).all()
+        assert np.abs(X).max() <= 1.0 + 1e-12 and np.abs(Y).max() <= 1.0 + 1e-12
+        outs.append((X, Y))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    X, Y = outs[0]
+    c = 100 * EPS * max(n, 8)
+    assert np.linalg.norm(X @ X.T - np.eye(n)) <= c and np.linalg.norm(Y @ Y.T - np.eye(n)) <= c
+    if n > 1:
+        assert np.linalg.norm(B - Y.T @ np.diag(sv) @ X) / np.linalg.norm(B) <= c
