@@ -608,6 +608,180 @@ finish_xf_kernel(double *__restrict__ A, long lda, int i, int m, int n, int k, i
     }
 }
 
+// The same step for long columns (more rows than one wave of 32-row blocks holds): 128 rows per CTA, all of
+// them in flight at once - warp w owns rows 32*(w&3).. of the block and the panel columns (w>>2) + 8z, z < 4
+// (panel width <= 32) - instead of RB 32-row groups one after the other: one pass through the
+// load -> reduce -> x,c' -> partial dots chain per CTA (finish_xf<4>: four).
+constexpr int XW_ROWS = 128, XW_SL = 8, XW_Z = 4;
+__global__ void __launch_bounds__(1024)
+finish_xw_kernel(double *__restrict__ A, long lda, int i, int m, int n, int k, int nb,
+                 double *__restrict__ P, long ldp, double *__restrict__ Q, long ldq,
+                 double *__restrict__ c, const double *__restrict__ rv,
+                 const double *__restrict__ tmp, long ldt, int nsplit,
+                 const double *__restrict__ dots2p, int nparts2, double *__restrict__ beta, int nRowBlk,
+                 int nGroups, double *__restrict__ dots1p)
+{
+    constexpr int S = DOT_SLOTS_C;
+    __shared__ double s_d[S];
+    __shared__ double s_yTu[NBMAX], s_uTu[NBMAX], s_rowY[NBMAX], s_rowU[NBMAX];
+    __shared__ double s_red[3][XW_SL][XW_ROWS + 1];
+    __shared__ double s_c[XW_ROWS], s_x[XW_ROWS];
+    __shared__ double s_o[4][2 * 32 + 1];
+    static_assert(15 * DOT_SLOTS_C <= 3 * XW_SL * (XW_ROWS + 1), "s_part does not fit into s_red");
+    double(*s_part)[S] = reinterpret_cast<double(*)[S]>(&s_red[0][0][0]);
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int rq = w & 3, sl = w >> 2, rr = rq * 32 + lane;
+    const int R = n - i - 1, Lb = m - i - 1;
+    const bool rowblk = (int)blockIdx.x < nRowBlk;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+    int idx = blockIdx.x * XW_ROWS + rr;
+    bool live = rowblk && idx < Lb;
+    double vk[XW_Z], xk[XW_Z], tt = 0.0, ar = 0.0;
+    auto load_group = [&]() {
+        tt = 0.0; ar = 0.0;
+#pragma unroll
+        for (int z = 0; z < XW_Z; ++z) {
+            const int q = sl + XW_SL * z;
+            vk[z] = (live && q <= k) ? P[(i + 1 + idx) + (long)q * ldp] : 0.0;
+            xk[z] = (live && q < k) ? P[(i + 1 + idx) + (long)(nb + q) * ldp] : 0.0;
+        }
+        if (live) {
+            // this slice's partials of the pass, ten in flight at a time (<= 80 clusters per round)
+            for (int sp0 = sl; sp0 < nsplit; sp0 += 10 * XW_SL) {
+                double tv[10];
+#pragma unroll
+                for (int u = 0; u < 10; ++u) {
+                    const int sp = sp0 + u * XW_SL;
+                    tv[u] = (sp < nsplit) ? tmp[(long)sp * ldt + i + 1 + idx] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 10; ++u) tt += tv[u];
+            }
+            if (sl == 0) ar = A[(i + 1 + idx) + (long)(i + 1) * lda];
+        }
+    };
+    load_group();
+    const double rf = rv[i + 1];
+    double qy = 0.0, qu = 0.0;
+    if (t <= k) qy = Q[(i + 1) + (long)t * ldq];
+    if (t < k) qu = Q[(i + 1) + (long)(nb + t) * ldq];
+    const int ne = 2 * k + 2;
+    const int TPE = (ne <= 68) ? 15 : 7;
+    {
+        const int e = t / TPE, part = t - TPE * e;
+        if (e < ne) {
+            const int slot = (e <= k) ? e : (e <= 2 * k ? nb + (e - k - 1) : 2 * nb);
+            const int chunk = (nparts2 + TPE - 1) / TPE, p0 = part * chunk, p1 = min(nparts2, p0 + chunk);
+            constexpr int LB = 10;
+            double a2 = 0.0;
+            for (int base = p0; base < p1; base += LB) {
+                double v[LB];
+#pragma unroll
+                for (int u = 0; u < LB; ++u) v[u] = (base + u < p1) ? dots2p[(long)(base + u) * S + slot] : 0.0;
+#pragma unroll
+                for (int u = 0; u < LB; ++u) a2 += v[u];
+            }
+            s_part[part][slot] = a2;
+        }
+    }
+    __syncthreads();
+    if (t < S && (t <= k || (t >= nb && t < nb + k) || t == 2 * nb)) {
+        double a2 = 0.0;
+        for (int pz = 0; pz < TPE; ++pz) a2 += s_part[pz][t];
+        s_d[t] = a2;
+    }
+    __syncthreads();
+    const Refl f = make_refl(rf, s_d[2 * nb]);
+    const double ufirst = (rf + f.snu) * f.inv;
+    if (!rowblk) {
+        const int cidx = (blockIdx.x - nRowBlk) * 1024 + t;
+        if (cidx == 0) beta[i] = -f.snu;
+        if (cidx < R) {
+            const int j = i + 1 + cidx;
+            const double u = (rv[j] + (cidx == 0 ? f.snu : 0.0)) * f.inv;
+            A[i + (long)j * lda] = u;
+            Q[j + (long)(nb + k) * ldq] = u;
+        }
+        return;
+    }
+    if (t <= k) { s_rowY[t] = qy; s_yTu[t] = (s_d[t] + f.snu * qy) * f.inv; }
+    if (t < k) { s_rowU[t] = qu; s_uTu[t] = (s_d[nb + t] + f.snu * qu) * f.inv; }
+    __syncthreads();
+
+    double dv[XW_Z], dx[XW_Z], cc2 = 0.0;
+#pragma unroll
+    for (int z = 0; z < XW_Z; ++z) { dv[z] = 0.0; dx[z] = 0.0; }
+#pragma unroll 1
+    for (int g = blockIdx.x; g < nGroups; g += nRowBlk) {
+        if (g != (int)blockIdx.x) {
+            idx = g * XW_ROWS + rr;
+            live = idx < Lb;
+            load_group();
+        }
+        const int r = i + 1 + idx;
+        double corr = 0.0, sub = 0.0;
+#pragma unroll
+        for (int z = 0; z < XW_Z; ++z) {
+            const int q = sl + XW_SL * z;
+            if (q <= k) { corr += vk[z] * s_yTu[q]; sub += vk[z] * s_rowY[q]; }
+            if (q < k) { corr += xk[z] * s_uTu[q]; sub += xk[z] * s_rowU[q]; }
+        }
+        s_red[0][sl][rr] = corr; s_red[1][sl][rr] = sub; s_red[2][sl][rr] = tt;
+        __syncthreads();
+        if (sl == 0) {                                      // warps 0..3: one row each
+            double cc = 0.0, x = 0.0;
+            if (live) {
+                corr = 0.0; sub = 0.0; tt = 0.0;
+#pragma unroll
+                for (int z = 0; z < XW_SL; ++z) { corr += s_red[0][z][rr]; sub += s_red[1][z][rr]; tt += s_red[2][z][rr]; }
+                x = 2.0 * ((tt + f.snu * ar) * f.inv - corr);
+                P[r + (long)(nb + k) * ldp] = x;
+                cc = ar - sub - x * ufirst;
+                c[r] = cc;
+            }
+            s_c[rr] = cc;
+            s_x[rr] = x;
+            cc2 += cc * cc;
+            if (g == 0 && t == 0) c[i] = 0.0;               // keeps the 128-bit loads of the next pass harmless
+        }
+        __syncthreads();
+        const double cl = s_c[rr];
+#pragma unroll
+        for (int z = 0; z < XW_Z; ++z) {
+            const int q = sl + XW_SL * z;
+            if (q <= k) {
+                const double xv = (q < k) ? xk[z] : s_x[rr];
+                dv[z] += vk[z] * cl;
+                dx[z] += xv * cl;
+            }
+        }
+    }
+    // ---- this CTA's partial [V^T c' | X^T c' | c'.c']: per warp, then over the four row quarters
+#pragma unroll
+    for (int z = 0; z < XW_Z; ++z) {
+        const int q = sl + XW_SL * z;
+        if (q <= k) {                                       // warp-uniform
+            const double a2 = warp_sum(dv[z]), b2 = warp_sum(dx[z]);
+            if (lane == 0) { s_o[rq][q] = a2; s_o[rq][32 + q] = b2; }
+        }
+    }
+    if (sl == 0) {
+        const double a2 = warp_sum(cc2);
+        if (lane == 0) s_o[rq][64] = a2;
+    }
+    __syncthreads();
+    double *out = dots1p + (long)blockIdx.x * S;
+    if (t < 65) {
+        const int q = t & 31;
+        if (t == 64 || q <= k) {
+            const double a2 = (s_o[0][t] + s_o[1][t]) + (s_o[2][t] + s_o[3][t]);
+            out[t == 64 ? 2 * nb : (t < 32 ? q : nb + q)] = a2;
+        }
+    }
+}
+
 __global__ void col_init_kernel(const double *__restrict__ A, int m, long lda, double *__restrict__ c)
 {
     long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -800,6 +974,19 @@ template <int RB, typename... Args> static void launch_finish_xf(int grid, cudaS
     cfg.attrs = at; cfg.numAttrs = g_pdl_f ? 1 : 0;
     SVD_CUDA_CHECK(cudaLaunchKernelEx(&cfg, finish_xf_kernel<RB>, args...));
 }
+template <typename... Args> static void launch_finish_xw(int grid, cudaStream_t st, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(1024);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = g_pdl_f ? 1 : 0;
+    SVD_CUDA_CHECK(cudaLaunchKernelEx(&cfg, finish_xw_kernel, args...));
+}
 static void launch_fused(const FusedArgs &fa, const FusedPlan &pl, cudaStream_t st)
 {
     switch (pl.RPT) {
@@ -982,6 +1169,7 @@ void bidiag_device(int m, int n, double *A, long lda, double *alpha, double *bet
     const char *e1 = getenv("SVD_GPU_FUSED_MIN_ROWS"), *e2 = getenv("SVD_GPU_FUSED_MIN_COLS");
     const int fz_min_rows = e1 ? atoi(e1) : FZ_MIN_ROWS, fz_min_cols = e2 ? atoi(e2) : FZ_MIN_COLS;
     // SVD_GPU_TAIL=0/1: finish on chip once the trailing block fits into shared memory (bidiag_tail.cuh)
+    const int xw_mode = getenv("SVD_GPU_XW") ? atoi(getenv("SVD_GPU_XW")) : 1;     // finish_xw: 0 never, 1 long columns, 2 always
     const char *tenv = getenv("SVD_GPU_TAIL");
     const bool use_tail = tenv ? (tenv[0] != '0') : (TAIL_DEFAULT_ON != 0);
     g_tail_mode = (tenv && tenv[0] == '1') ? 1 : 2;
@@ -1080,9 +1268,16 @@ void bidiag_device(int m, int n, double *A, long lda, double *alpha, double *bet
                 static const int old_rule = getenv("SVD_GPU_XF_OLD") ? 1 : 0;      // experiments
                 const int rb = old_rule ? (Lb > 4096 ? 4 : 1)
                                         : (Lb <= 32 * (nsm - nColBlk)) ? 1 : (Lb <= 64 * (nsm - nColBlk)) ? 2 : 4;
-                const int nRowBlk = ceil_div(Lb, 32 * rb);
+                // SVD_GPU_XW: 0 = never the 128-rows-at-once kernel, 1 = where rb would exceed 1, 2 = always
+                const bool wide = nb <= 32 && (xw_mode == 2 || (xw_mode == 1 && rb > 1));
+                const int nGroups = ceil_div(Lb, XW_ROWS);
+                const int nRowBlk = wide ? std::max(1, std::min(nGroups, nsm - nColBlk)) : ceil_div(Lb, 32 * rb);
                 prof.begin(1, i, st);
-                if (rb == 1)
+                if (wide)
+                    launch_finish_xw(nRowBlk + nColBlk, st, A, lda, i, m, n, k, nb, b.P, b.ldp, b.Q, b.ldq, b.c,
+                                     (const double *)b.rv, (const double *)b.tmpN, lda, pl.NC,
+                                     (const double *)b.dots2p, pl.NC, beta, nRowBlk, nGroups, b.dots1p);
+                else if (rb == 1)
                     launch_finish_xf<1>(nRowBlk + nColBlk, st, A, lda, i, m, n, k, nb, b.P, b.ldp, b.Q, b.ldq, b.c,
                                         (const double *)b.rv, (const double *)b.tmpN, lda, pl.NC,
                                         (const double *)b.dots2p, pl.NC, beta, nRowBlk, b.dots1p);

@@ -111,9 +111,11 @@ def test_bidiag_panel_width_invariance(D, nb):
 
 
 @pytest.mark.parametrize("shape", [(1500, 1400), (4200, 300), (8704, 256), (16500, 130), (33000, 100)])
-def test_bidiag_fused_pass_vs_oracle(D, shape):
+@pytest.mark.parametrize("xw", ["1", "0", "2"])     # finish_xw (128 rows per CTA at once): long columns / never / always
+def test_bidiag_fused_pass_vs_oracle(D, shape, xw, monkeypatch):
     # tall enough for the fused single-read pass (bidiag_fused.cuh): 1 CTA per column tile up to
     # 8192 rows, clusters of 2 / 4 / 8 CTAs (DSMEM exchange) above
+    monkeypatch.setenv("SVD_GPU_XW", xw)
     m, n = shape
     A = util.rand_matrix(m, n, 1.0, 2.0, 4)
     Ao, ao, bo = util.oracle_bidiag(A)
