@@ -333,15 +333,16 @@ def measure(E, n, steps, warmup, e2e_steps, want_probe, want_pageable):
             del U1, V1
         barrier()
 
-    # ---- roofline of the dominant kernels (N = 1)
-    if world == 1:
-        ph = [0, res["phases"]["bidiag_ms"], 0, 0, res["phases"]["backtransform_ms"]]
+    # ---- roofline of the dominant kernels (at N > 1: rank 0's factorization, the slowest rank's back-transform)
+    if True:
+        ph = [0, res["phases"]["bidiag_ms"], 0, 0,
+              res["phases"]["backtransform_ms"] if world == 1 else res["phases"]["backtransform_ms_max"]]
         pk, which = peaks()
         fused_on = os.environ.get("SVD_GPU_FUSED", "1") != "0"
         tail_on = os.environ.get("SVD_GPU_TAIL", "1") != "0"
         b_own, b_survey = bidiag_bytes(m, n, nb, fused_on, tail_on)
         probe = {}
-        if want_probe:
+        if want_probe and world == 1:
             wbytes = L.svdgpu_bidiag_workspace(m, n, m)
             work = torch.zeros(wbytes // 8 + 8, dtype=torch.float64, device=dev)
             scratchA = A_master.clone()            # the fused probe writes a reflector into column 0
@@ -366,7 +367,7 @@ def measure(E, n, steps, warmup, e2e_steps, want_probe, want_pageable):
         t_bd = ph[1] * 1e-3
         ach_survey = b_survey / t_bd / 1e9          # SURVEY.md 8(d) definition: B_alg = 8 * 1.5 * S
         ach_own = b_own / t_bd / 1e9                # bytes our scheme actually has to move
-        bt = backxf_flops(m, n) / (ph[4] * 1e-3) / 1e12
+        bt = backxf_flops(m, n) / world / (ph[4] * 1e-3) / 1e12       # per GPU
         res["roofline"] = {
             "bound": "hbm",
             "kernel": ("fused_pass_kernel (single-read pass) + finish_xf + panel GEMM (dgemm_ws_kernel); bidiag_tail_kernel "
