@@ -19,7 +19,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsvdgpu.so")
+LIB_PATH = os.environ.get("SVD_GPU_LIB") or os.path.join(_HERE, "libsvdgpu.so")   # SVD_GPU_LIB: A/B builds (bench/ab_build.sh)
 _lib = None
 
 c_double_p = ctypes.POINTER(ctypes.c_double)

@@ -791,6 +791,7 @@ __global__ void col_init_kernel(const double *__restrict__ A, int m, long lda, d
 } // namespace svdgpu
 #include "bidiag_fused.cuh"
 #include "bidiag_tail.cuh"
+#include "bidiag_panel.cuh"
 namespace svdgpu {
 static_assert(TAIL_WS_SLOTS == TL_WS_SLOTS, "workspace sizing of the on-chip tail");
 
@@ -1030,6 +1031,37 @@ static void fused_set_attributes()
     if (fc) force_cs = atoi(fc);
 }
 
+// ---- persistent per-panel kernel (bidiag_panel.cuh)
+static int g_panel_ctas = -1;           // co-resident CTAs of the panel kernel (0: not available)
+static void panel_init(int nsm)
+{
+    static DeviceOnce once;
+    if (!first_on_device(once)) return;
+    int per = 0;
+    g_panel_ctas = 1 << 30;
+    const void *fns[3] = {(const void *)panel_kernel<2>, (const void *)panel_kernel<4>, (const void *)panel_kernel<8>};
+    for (int z = 0; z < 3; ++z) {
+        if (cudaFuncSetAttribute(fns[z], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FZ_SMEM_BYTES) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, fns[z], FZ_THREADS, FZ_SMEM_BYTES) != cudaSuccess) {
+            (void)cudaGetLastError();
+            per = 0;
+        }
+        g_panel_ctas = std::min(g_panel_ctas, per * nsm);
+    }
+    int coop = 0, dev = 0;
+    SVD_CUDA_CHECK(cudaGetDevice(&dev));
+    SVD_CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    if (!coop) g_panel_ctas = 0;
+}
+static void launch_panel(const PanelArgs &pa, int RPT, cudaStream_t st)
+{
+    SVD_CUDA_CHECK(cudaMemsetAsync(pa.bar, 0, sizeof(unsigned), st));
+    void *args[] = {(void *)&pa};
+    const void *fn = RPT == 2 ? (const void *)panel_kernel<2> : RPT == 4 ? (const void *)panel_kernel<4> : (const void *)panel_kernel<8>;
+    SVD_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(pa.NC), dim3(FZ_THREADS), args, FZ_SMEM_BYTES, st));
+    SVD_KERNEL_CHECK();
+}
+
 // ---- on-chip tail (bidiag_tail.cuh): from step i on, if the trailing block fits the SMs' shared memory
 static int g_tail_ctas = -1;            // co-resident CTAs of the tail kernel (0: not available)
 static bool g_tail2_ok = false;
@@ -1170,6 +1202,9 @@ void bidiag_device(int m, int n, double *A, long lda, double *alpha, double *bet
     const int fz_min_rows = e1 ? atoi(e1) : FZ_MIN_ROWS, fz_min_cols = e2 ? atoi(e2) : FZ_MIN_COLS;
     // SVD_GPU_TAIL=0/1: finish on chip once the trailing block fits into shared memory (bidiag_tail.cuh)
     const int xw_mode = getenv("SVD_GPU_XW") ? atoi(getenv("SVD_GPU_XW")) : 1;     // finish_xw: 0 never, 1 long columns, 2 always
+    // SVD_GPU_PPK=1: whole panels of single-CTA passes in one persistent cooperative launch (bidiag_panel.cuh)
+    const bool use_ppk = use_fused && (getenv("SVD_GPU_PPK") ? atoi(getenv("SVD_GPU_PPK")) != 0 : PPK_DEFAULT_ON);
+    if (use_ppk) panel_init(nsm);
     const char *tenv = getenv("SVD_GPU_TAIL");
     const bool use_tail = tenv ? (tenv[0] != '0') : (TAIL_DEFAULT_ON != 0);
     g_tail_mode = (tenv && tenv[0] == '1') ? 1 : 2;
@@ -1219,6 +1254,61 @@ void bidiag_device(int m, int n, double *A, long lda, double *alpha, double *bet
 
         FusedPlan pl = {false, 1, 4, 0, 0, 0};
         if (use_fused && !tail && do_col && do_row) pl = plan_fused(i, m, n, mpad, nsm, fz_min_rows < 2 ? 2 : fz_min_rows, fz_min_cols < 1 ? 1 : fz_min_cols);
+        // a whole panel at once: every step of it a regular single-CTA fused step with at least one tile per CTA
+        if (pl.ok && use_ppk && k == 0 && pl.CS == 1 && nb <= 32 && g_panel_ctas > 0 && pl.NC <= g_panel_ctas &&
+            i + nb < mn - 1 && i + nb < n - 2 && n - (i + nb) >= pl.NC * FZ_CBW_MAX && m - (i + nb) >= 64 &&
+            ceil_div(Lb, 32) < pl.NC && (!hook || !hook->fn || hook->every <= 0 || hook->every % nb == 0)) {
+            if (!dots1_ready) {
+                gemvT_kernel<<<dim3(1, 1), GT_WARPS * 32, 0, st>>>(A, lda, i, m, n, mpad, b.c, b.tmpT, b.ldq,
+                                                                   0, 0, b.P, b.ldp, nb, 0, b.dots1);
+                SVD_KERNEL_CHECK();
+            }
+            PanelArgs pa;
+            pa.A = A; pa.lda = lda; pa.i0 = i; pa.k0 = 0; pa.nsteps = nb; pa.m = m; pa.n = n; pa.mpad = mpad; pa.nb = nb;
+            pa.P = b.P; pa.ldp = b.ldp; pa.Q = b.Q; pa.ldq = b.ldq; pa.c = b.c; pa.rv = b.rv;
+            pa.tmpN = b.tmpN; pa.ldt = lda;
+            pa.dots1 = dots1_ready ? b.dots1p : b.dots1; pa.nparts1 = dots1_ready ? dots1_parts : 0;
+            pa.dots1p = b.dots1p; pa.dots2p = b.dots2p; pa.alpha = alpha; pa.beta = beta;
+            pa.NC = pl.NC; pa.Lc = pl.Lc; pa.bar = b.counters + 12;
+            pa.trace = nullptr;
+            static unsigned long long *d_ptrace = nullptr;
+            const char *pte = getenv("SVD_GPU_PPK_TRACE");
+            const bool ptracing = pte && atoi(pte) == i;
+            if (ptracing) {
+                if (!d_ptrace) SVD_CUDA_CHECK(cudaMalloc(&d_ptrace, 8 * (NBMAX + 64) * sizeof(unsigned long long)));
+                SVD_CUDA_CHECK(cudaMemsetAsync(d_ptrace, 0, 8 * (NBMAX + 64) * sizeof(unsigned long long), st));
+                pa.trace = d_ptrace;
+            }
+            prof.begin(0, i, st);
+            launch_panel(pa, pl.RPT, st);
+            prof.end(st);
+            if (ptracing) {
+                static unsigned long long h[8 * (NBMAX + 64)];
+                SVD_CUDA_CHECK(cudaMemcpyAsync(h, d_ptrace, sizeof h, cudaMemcpyDeviceToHost, st));
+                SVD_CUDA_CHECK(cudaStreamSynchronize(st));
+                fprintf(stderr, "PPKTRACE panel at step %d RPT %d Lc %d NC %d: per step, cycles since the step's start: prologue end | "
+                                "pass done in CTA 0 | barrier 1 passed | finish done | barrier 2 passed | first TMA | last TMA | step length\n",
+                        i, pl.RPT, pl.Lc, pl.NC);
+                for (int z = 0; z < nb; ++z) {
+                    const unsigned long long t0 = h[z * 8];
+                    fprintf(stderr, "PPKTRACE %2d", z);
+                    for (int q = 1; q < 8; ++q) fprintf(stderr, " %7lld", h[z * 8 + q] ? (long long)(h[z * 8 + q] - t0) : -1ll);
+                    fprintf(stderr, " %7lld\n", z + 1 < nb ? (long long)(h[(z + 1) * 8] - t0) : -1ll);
+                }
+                fprintf(stderr, "PPKTILE step %d, per tile of CTA 0, cycles since that step's start: TMA issue | sweep-1 start | sweep-1 done | "
+                                "reducer | finisher start | finisher done | sweep-2 start | sweep-2 done\n", i + 1);
+                for (int nt = 0; nt < 64 && h[(NBMAX + nt) * 8 + 1]; ++nt) {
+                    fprintf(stderr, "PPKTILE %2d", nt);
+                    for (int q = 0; q < 8; ++q)
+                        fprintf(stderr, " %7lld", h[(NBMAX + nt) * 8 + q] ? (long long)(h[(NBMAX + nt) * 8 + q] - h[8]) : -1ll);
+                    fprintf(stderr, "\n");
+                }
+            }
+            i += nb - 1;
+            k = nb - 1;
+            dots1_ready = true;
+            dots1_parts = ceil_div(m - i - 1, 32);
+        } else
         if (pl.ok) {
             g_pdl = (g_pdl_mode == 2) || (g_pdl_mode == 1 && pl.CS <= g_pdl_cs);
             g_pdl_f = (g_pdl_mode == 2) || (g_pdl_mode == 1 && (pl.CS <= g_pdl_cs || g_pdl_fin));

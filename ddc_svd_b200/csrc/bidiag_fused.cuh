@@ -14,7 +14,7 @@
 //   * the tile (<= 32 KB per stage, 6 stages: two tiles being consumed, four in flight) is brought in by TMA bulk copies
 //     (cp.async.bulk ... mbarrier::complete_tx), one per column segment, issued by an elected
 //     lane of a dedicated producer warp; full/empty mbarriers form the pipeline;
-//   * helper warps gather, while the copies fly, the tile's panel rows (Y[j,:], U[j,:]) and reduce
+//   * helper warps (3) gather, while the copies fly, the tile's panel rows (Y[j,:], U[j,:]) and reduce
 //     the 2k-term corrections that y_j / r_j need;
 //   * the two sweeps are done by DIFFERENT warps connected only by mbarriers (no CTA-wide barrier
 //     in the loop): 8 sweep-1 warps (c in registers) hand their column sums to a reducer warp, a
@@ -36,7 +36,24 @@ constexpr int FZ_STAGE = 4096;            // doubles per shared-memory stage (32
 constexpr int FZ_STAGES = 6;
 constexpr int FZ_CBW_MAX = 4;             // columns per tile (rows per CTA <= 1024 -> 4 columns)
 constexpr int FZ_XR = 16;                 // ring depth of the cross-CTA exchange (>= 2*FZ_STAGES)
-constexpr int FZ_HW = 2;                  // helper warps (tile n is prepared by helper n % FZ_HW)
+// compile-time switches for A/B builds on the same box (bench/ab_build.sh); the defaults are the measured best
+// (profiles/r02_ab_helper_warps.log: 3 helper warps instead of 2 = -2.8 % at 16384^2, -4.3 % at 8192^2, -1.2 % at
+// 4096^2 - two helpers, each a trip to L2 per tile, could not keep up with the stream; 4 and 5 are slower again;
+// batching the sweeps' shared-memory loads is neutral; requesting a step's first panel rows before the prologue
+// costs more in registers than it hides)
+#ifndef SVDGPU_FZ_HW
+#define SVDGPU_FZ_HW 3
+#endif
+#ifndef SVDGPU_FZ_BATCH
+#define SVDGPU_FZ_BATCH 4
+#endif
+#ifndef SVDGPU_FZ_WP
+#define SVDGPU_FZ_WP 1
+#endif
+#ifndef SVDGPU_FZ_EARLY
+#define SVDGPU_FZ_EARLY 0
+#endif
+constexpr int FZ_HW = SVDGPU_FZ_HW;       // helper warps (tile n is prepared by helper n % FZ_HW)
 constexpr int FZ_GW = 8;                  // warps per sweep group
 constexpr int FZ_GT = FZ_GW * 32;         // threads per sweep group
 // warp roles: 0 TMA producer | 1..HW helpers | HW+1 reducer | NFIN finishers |
@@ -166,12 +183,60 @@ __device__ __forceinline__ void fz_cluster_sync()
                  "barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
 
+
+// ---- the two inner products of a tile column, per sweep thread ---------------------------------
+// The shared-memory loads are issued four at a time into distinct registers before the FMAs that use them: with
+// one destination register set (what the compiler falls back to under the 80-register cap of a 24-warp CTA) every
+// LDS waits for the FMAs of the previous one and a 4096-row column costs ~8 x (LDS + DFMA) latencies per tile.
+template <int RPT>
+__device__ __forceinline__ double fz_col_dot(const double *__restrict__ col, const double2 (&creg)[RPT], int gt, int len)
+{
+    constexpr int B = RPT < SVDGPU_FZ_BATCH ? RPT : SVDGPU_FZ_BATCH;
+    double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;      // independent chains (same order as ever: results unchanged)
+#pragma unroll
+    for (int u0 = 0; u0 < RPT; u0 += B) {
+        double2 av[B];
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            const int lr = 2 * gt + 2 * FZ_GT * (u0 + b);
+            av[b] = (lr < len) ? *reinterpret_cast<const double2 *>(col + lr) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            const int u = u0 + b;
+            if (u & 1) { p2 += av[b].x * creg[u].x; p3 += av[b].y * creg[u].y; }
+            else       { p0 += av[b].x * creg[u].x; p1 += av[b].y * creg[u].y; }
+        }
+    }
+    return (p0 + p1) + (p2 + p3);
+}
+template <int RPT>
+__device__ __forceinline__ void fz_col_axpy(const double *__restrict__ col, double r, double2 (&acc)[RPT], int gt, int len)
+{
+    constexpr int B = RPT < SVDGPU_FZ_BATCH ? RPT : SVDGPU_FZ_BATCH;
+#pragma unroll
+    for (int u0 = 0; u0 < RPT; u0 += B) {
+        double2 av[B];
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            const int lr = 2 * gt + 2 * FZ_GT * (u0 + b);
+            av[b] = (lr < len) ? *reinterpret_cast<const double2 *>(col + lr) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            acc[u0 + b].x += av[b].x * r;
+            acc[u0 + b].y += av[b].y * r;
+        }
+    }
+}
+
 #define FZ_TR(slot, nt) do { if (a.trace && blockIdx.x == 0 && (nt) < 256) a.trace[(nt) * 8 + (slot)] = clock64(); } while (0)
 // RPT = row pairs per sweep thread (rows per CTA <= 512*RPT <= 4096), CBW = 8/RPT columns per tile
 template <int RPT>
 __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedArgs a)
 {
     constexpr int CBW = 8 / RPT;
+    constexpr int WP = SVDGPU_FZ_WP ? FZ_CBW_MAX / CBW : 1;    // lane partials each sweep-1 warp leaves per column (fills the same 32 slots per stage)
     extern __shared__ __align__(128) unsigned char fz_smem[];
     double *tile = reinterpret_cast<double *>(fz_smem);
     double *qrow = tile + (size_t)FZ_STAGES * FZ_STAGE;
@@ -256,6 +321,29 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
             const int lr = 2 * gt0 + 2 * FZ_GT * u;
             creg[u] = (lr < len) ? *reinterpret_cast<const double2 *>(a.c + rs + lr) : make_double2(0.0, 0.0);
         }
+    }
+    // helper warps: the panel rows of their FIRST tile are requested now, so that the trip to L2 overlaps the
+    // prologue below instead of following it (a step's first tile used to become ready ~3 us after the prologue)
+    constexpr bool EARLY = SVDGPU_FZ_EARLY && (CBW <= 2);          // four columns per tile: 20 doubles would spill
+    double hy0[EARLY ? CBW : 1][2], hu0[EARLY ? CBW : 1][2], ha0[EARLY ? CBW : 1];
+    auto helper_load = [&](int nt, double (&yy)[CBW][2], double (&uu)[CBW][2], double (&aa)[CBW]) {
+        const int j0 = i + 1 + (g + nt * NC) * CBW;
+        int ncols = a.n - j0;
+        if (ncols > CBW) ncols = CBW;
+#pragma unroll
+        for (int q = 0; q < CBW; ++q) {
+            const int j = (q < ncols) ? j0 + q : j0;
+            aa[q] = (lane == 0) ? a.A[i + (long)j * a.lda] : 0.0;
+#pragma unroll
+            for (int z = 0; z < 2; ++z) {
+                const int kk = lane + 32 * z;
+                yy[q][z] = (kk < k) ? a.Q[j + (long)kk * a.ldq] : 0.0;
+                uu[q][z] = (kk < k) ? a.Q[j + (long)(nb + kk) * a.ldq] : 0.0;
+            }
+        }
+    };
+    if constexpr (EARLY) {
+        if (warp >= 1 && warp <= FZ_HW && warp - 1 < ntiles) helper_load(warp - 1, hy0, hu0, ha0);
     }
     // ---- combine the partial dots of the current column c (left by finish_xf) in a fixed order;
     //      the panel-row area is still unused and serves as scratch (the tiles may already be in flight)
@@ -345,16 +433,17 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
             int ncols = a.n - j0;
             if (ncols > CBW) ncols = CBW;
             double yk[CBW][2], uk[CBW][2], aij[CBW];
+            if (EARLY && nt == warp - 1) {
+                if constexpr (EARLY) {
 #pragma unroll
-            for (int q = 0; q < CBW; ++q) {
-                const int j = (q < ncols) ? j0 + q : j0;
-                aij[q] = (lane == 0) ? a.A[i + (long)j * a.lda] : 0.0;
+                    for (int q = 0; q < CBW; ++q) {
+                        aij[q] = ha0[q];
 #pragma unroll
-                for (int z = 0; z < 2; ++z) {
-                    const int kk = lane + 32 * z;
-                    yk[q][z] = (kk < k) ? a.Q[j + (long)kk * a.ldq] : 0.0;
-                    uk[q][z] = (kk < k) ? a.Q[j + (long)(nb + kk) * a.ldq] : 0.0;
+                        for (int z = 0; z < 2; ++z) { yk[q][z] = hy0[q][z]; uk[q][z] = hu0[q][z]; }
+                    }
                 }
+            } else {
+                helper_load(nt, yk, uk, aij);
             }
             fz_mbar_wait(empty + s, ((nt / FZ_STAGES) & 1) ^ 1);     // stage (and its helper slots) free
 #pragma unroll
@@ -391,10 +480,10 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
             double vals[CBW];
 #pragma unroll
             for (int qq = 0; qq < CBW; ++qq) {
-                double v = (lane < FZ_GW) ? wsum[(s * FZ_GW + lane) * FZ_CBW_MAX + qq] : 0.0;
-                v += __shfl_xor_sync(0xffffffffu, v, 1);
-                v += __shfl_xor_sync(0xffffffffu, v, 2);
-                v += __shfl_xor_sync(0xffffffffu, v, 4);
+                // FZ_WP partials per sweep-1 warp: 8 * FZ_WP values per column
+                double v = (lane < FZ_GW * WP) ? wsum[s * (FZ_GW * FZ_CBW_MAX) + qq * (FZ_GW * WP) + lane] : 0.0;
+#pragma unroll
+                for (int off = FZ_GW * WP / 2; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
                 vals[qq] = __shfl_sync(0xffffffffu, v, 0);
             }
             if (CS == 1) {
@@ -528,20 +617,13 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
             const double *tl = tile + (size_t)s * FZ_STAGE;
 #pragma unroll
             for (int q = 0; q < CBW; ++q) {
-                double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;      // independent chains
-                if (q < ncols) {
+                const double pq = (q < ncols) ? fz_col_dot<RPT>(tl + (size_t)q * Lc, creg, gt, len) : 0.0;
+                // the last log2(WP) rounds of the lane reduction are left to the reducer warp (it has slack, this warp is
+                // the pipeline's critical role): lanes 0..WP-1 hold the partial sums of the lanes congruent to them mod WP
+                double ps = pq;
 #pragma unroll
-                    for (int u = 0; u < RPT; ++u) {
-                        const int lr = 2 * gt + 2 * FZ_GT * u;
-                        if (lr < len) {
-                            const double2 av = *reinterpret_cast<const double2 *>(tl + (size_t)q * Lc + lr);
-                            if (u & 1) { p2 += av.x * creg[u].x; p3 += av.y * creg[u].y; }
-                            else       { p0 += av.x * creg[u].x; p1 += av.y * creg[u].y; }
-                        }
-                    }
-                }
-                const double ps = warp_sum((p0 + p1) + (p2 + p3));
-                if (lane == 0) wsum[(s * FZ_GW + wig) * FZ_CBW_MAX + q] = ps;
+                for (int off = 16; off >= WP; off >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, off);
+                if (lane < WP) wsum[s * (FZ_GW * FZ_CBW_MAX) + q * (FZ_GW * WP) + wig * WP + lane] = ps;
             }
             __syncwarp();
             if (wig == 0 && lane == 0) FZ_TR(2, nt);
@@ -563,18 +645,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
             const double *tl = tile + (size_t)s * FZ_STAGE;
 #pragma unroll
             for (int q = 0; q < CBW; ++q) {
-                if (q < ncols) {
-                    const double r = rq[s * FZ_CBW_MAX + q];
-#pragma unroll
-                    for (int u = 0; u < RPT; ++u) {
-                        const int lr = 2 * gt + 2 * FZ_GT * u;
-                        if (lr < len) {
-                            const double2 av = *reinterpret_cast<const double2 *>(tl + (size_t)q * Lc + lr);
-                            acc[u].x += av.x * r;
-                            acc[u].y += av.y * r;
-                        }
-                    }
-                }
+                if (q < ncols) fz_col_axpy<RPT>(tl + (size_t)q * Lc, rq[s * FZ_CBW_MAX + q], acc, gt, len);
             }
             __syncwarp();
             if (wig == 0 && lane == 0) FZ_TR(7, nt);

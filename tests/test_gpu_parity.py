@@ -622,3 +622,28 @@ def test_svd_gpu_4096_properties(D):
     assert np.linalg.norm(A - (U * sigma) @ V.T) / np.linalg.norm(A) <= 100 * e
     # checksum of checksums: ||A||_F^2 = sum sigma^2
     assert abs(np.sum(sigma ** 2) - np.sum(A ** 2)) <= 100 * e * np.sum(A ** 2)
+
+
+@pytest.mark.parametrize("shape", [(1500, 1400), (2500, 2500), (3000, 1000), (2000, 3000), (4096, 4096), (4100, 1800)])
+@pytest.mark.parametrize("tail", ["0", "2"])
+def test_bidiag_persistent_panel_kernel(D, shape, tail, monkeypatch):
+    # bidiag_panel.cuh: all the steps of a panel in ONE cooperative launch (pass -> grid barrier -> finish -> grid
+    # barrier), the TMA producer streaming across the barriers.  Same arithmetic as the two-kernel path: the results
+    # must agree with it to rounding, and with the oracle where the CPU restatement finishes in seconds.
+    m, n = shape
+    A = util.rand_matrix(m, n, 1.0, 2.0, 4)
+    monkeypatch.setenv("SVD_GPU_TAIL", tail)
+    monkeypatch.setenv("SVD_GPU_PPK", "1")
+    Ag, ag, bg = D.bidiag_par(A)
+    monkeypatch.setenv("SVD_GPU_PPK", "0")
+    A0, a0, b0 = D.bidiag_par(A)
+    assert not np.isnan(Ag).any()
+    # (the finish splits its 2k-term corrections 16 ways instead of 32: last-bit differences, amplified by the
+    #  factorization like any rounding error)
+    assert np.abs(Ag - A0).max() <= 2e-10 and np.abs(ag - a0).max() <= 2e-10 * np.abs(a0).max()
+    assert np.abs(bg - b0).max() <= 2e-10 * max(1.0, np.abs(b0).max())
+    fro2 = float(np.sum(A * A))
+    assert abs(float(np.sum(ag * ag) + np.sum(bg * bg)) - fro2) <= 1e-12 * fro2      # ||B||_F = ||A||_F
+    if m * n <= 2500 * 2500:
+        Ao, ao, bo = util.oracle_bidiag(A)
+        assert np.abs(Ag - Ao).max() <= 1e-9 and np.abs(ag - ao).max() <= 1e-9 and np.abs(bg - bo).max() <= 1e-9
