@@ -3,7 +3,7 @@
 Covers the fused pass (clusters of 1 and 2 via SVD_GPU_FUSED_CS), the split passes, QR first, the
 wide-as-transpose route, values only, the phase entry points, and - second loop - the kernels behind the
 SVD_GPU_TAIL / SVD_GPU_GEMM_WS switches (on-chip tail on and off, persistent and one-tile-per-CTA GEMM), and
-- round 2 - the on-device checker, the progressive panel set-up, a group of one rank and the tcgen05 update.
+- round 2 - the on-device checker, the progressive panel set-up, a group of one rank, the tcgen05 update, the persistent per-panel kernel.
 (racecheck does not follow cross-CTA traffic through global memory: the tail kernel's exchange protocol is
 argued in bidiag_tail.cuh and exercised by test_bidiag_on_chip_tail.)"""
 import os, sys
@@ -63,4 +63,11 @@ L.svdgpu_d2h(util.p(out), bufs[2], out.nbytes, None); L.svdgpu_stream_sync(None)
 assert np.abs(out - (Cm - Am @ Bm)).max() <= 1e-11
 for d in bufs:
     L.svdgpu_free(d)
+# the persistent per-panel kernel (opt-in) and the 128-row finish kernel, streaming path to the end
+os.environ["SVD_GPU_PPK"] = "1"; os.environ["SVD_GPU_TAIL"] = "0"; os.environ["SVD_GPU_XW"] = "2"
+A = util.rand_matrix(1200, 1000)
+Am, al, be = D.bidiag_par(A)
+fro2 = float(np.sum(A * A))
+assert abs(float(np.sum(al * al) + np.sum(be * be)) - fro2) <= 1e-12 * fro2
+del os.environ["SVD_GPU_PPK"], os.environ["SVD_GPU_TAIL"], os.environ["SVD_GPU_XW"]
 print("round-2 paths ok", flush=True)
