@@ -897,12 +897,18 @@ static int sm_targets(int &targetT, int &targetN)
 
 
 // ---- fused pass launch (cluster launch, TMA/mbarrier kernel of bidiag_fused.cuh) ---------------
-struct FusedPlan { bool ok; int CS, RPT, Lc, T, NC; };
-static int g_max_clusters[3][FZ_MAXCS + 1];   // [RPT index][cluster size]: co-resident clusters (occupancy API)
+struct FusedPlan { bool ok; int CS, RPT, Lc, T, NC, var; };
+// kernel variants: 0 <2,4,6>  1 <4,2,6>  2 <8,1,6> (classic: 8/RPT columns per 32 KB stage)  3 <8,2,4> (two columns of up to
+// 3072 rows per 48 KB stage)
+constexpr int FZ_NVAR = 4;
+static const int fz_var_rpt[FZ_NVAR] = {2, 4, 8, 8}, fz_var_cbw[FZ_NVAR] = {4, 2, 1, 2};
+static int g_max_clusters[FZ_NVAR][FZ_MAXCS + 1];   // [variant][cluster size]: co-resident clusters (occupancy API)
+static bool g_fz_wide = false;          // SVD_GPU_FZ_WIDE=1: variant 3 for 2048 < rows per CTA <= 3072 (measured neutral to
+                                        // -0.6 %: the cost of a tile scales with its columns, profiles/r02_ab_helper_warps.log)
 static int force_cs = 0;
-static FusedPlan plan_fused(int i, int m, int n, int mpad, int nsm, int min_rows, int min_cols)
+static FusedPlan plan_fused(int i, int m, int n, int mpad, int nsm, int min_rows, int min_cols, bool classic = false)
 {
-    FusedPlan p = {false, 1, 4, 0, 0, 0};
+    FusedPlan p = {false, 1, 4, 0, 0, 0, 1};
     const int L = m - i, R = n - i - 1;
     if (L < min_rows || R < min_cols) return p;
     const int Ltot = mpad - (i & ~1);
@@ -915,9 +921,9 @@ static FusedPlan plan_fused(int i, int m, int n, int mpad, int nsm, int min_rows
         const int Lc = (int)round_up(ceil_div(Ltot, CS), 2);
         if (Lc > FZ_STAGE) continue;
         if (force_cs > 0 && CS != force_cs) continue;
-        int RPT = 2, ri = 0;
-        while (512 * RPT < Lc) { RPT *= 2; ++ri; }
-        const int cbw = 8 / RPT;
+        int ri = Lc <= 1024 ? 0 : Lc <= 2048 ? 1 : 2;
+        if (ri == 2 && Lc <= 3072 && g_fz_wide && !classic) ri = 3;
+        const int RPT = fz_var_rpt[ri], cbw = fz_var_cbw[ri];
         const int T = ceil_div(R, cbw);
         int maxc = g_max_clusters[ri][CS];
         if (maxc <= 0) continue;
@@ -927,7 +933,7 @@ static FusedPlan plan_fused(int i, int m, int n, int mpad, int nsm, int min_rows
         const double score = (double)NC * CS - 1e-3 * CS;
         if (score > best) {
             best = score;
-            p.CS = CS; p.Lc = Lc; p.RPT = RPT; p.T = T; p.NC = NC;
+            p.CS = CS; p.Lc = Lc; p.RPT = RPT; p.T = T; p.NC = NC; p.var = ri;
         }
     }
     p.ok = (best > 0.0 && p.NC >= 1);
@@ -945,7 +951,7 @@ static int g_pdl_cs = 2;        // largest cluster size whose pass is launched a
 static int g_pdl_fin = 1;       // finish_xf as a programmatic dependent of a clustered pass (SVD_GPU_PDL_FIN)
 static bool g_pdl = true;       // the decision for the pass launch of the current step
 static bool g_pdl_f = true;     // ... and for its finish_xf
-template <int RPT> static void launch_fused_t(const FusedArgs &fa, const FusedPlan &pl, cudaStream_t st)
+template <int RPT, int CBW, int NST> static void launch_fused_t(const FusedArgs &fa, const FusedPlan &pl, cudaStream_t st)
 {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(pl.NC * pl.CS);
@@ -958,7 +964,7 @@ template <int RPT> static void launch_fused_t(const FusedArgs &fa, const FusedPl
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = g_pdl ? 2 : 1;
-    SVD_CUDA_CHECK(cudaLaunchKernelEx(&cfg, fused_pass_kernel<RPT>, fa));
+    SVD_CUDA_CHECK(cudaLaunchKernelEx(&cfg, fused_pass_kernel<RPT, CBW, NST>, fa));
     SVD_KERNEL_CHECK();
 }
 // finish_xf as the programmatic dependent of the fused pass
@@ -990,13 +996,14 @@ template <typename... Args> static void launch_finish_xw(int grid, cudaStream_t 
 }
 static void launch_fused(const FusedArgs &fa, const FusedPlan &pl, cudaStream_t st)
 {
-    switch (pl.RPT) {
-    case 2: launch_fused_t<2>(fa, pl, st); break;
-    case 4: launch_fused_t<4>(fa, pl, st); break;
-    default: launch_fused_t<8>(fa, pl, st); break;
+    switch (pl.var) {
+    case 0: launch_fused_t<2, 4, 6>(fa, pl, st); break;
+    case 1: launch_fused_t<4, 2, 6>(fa, pl, st); break;
+    case 3: launch_fused_t<8, 2, 4>(fa, pl, st); break;
+    default: launch_fused_t<8, 1, 6>(fa, pl, st); break;
     }
 }
-template <int RPT> static void query_clusters_t(int ri)
+template <int RPT, int CBW, int NST> static void query_clusters_t(int ri)
 {
     for (int CS = 1; CS <= FZ_MAXCS; ++CS) {
         cudaLaunchConfig_t cfg = {};
@@ -1008,7 +1015,7 @@ template <int RPT> static void query_clusters_t(int ri)
         at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         int nc = 0;
-        if (cudaOccupancyMaxActiveClusters(&nc, fused_pass_kernel<RPT>, &cfg) != cudaSuccess) { nc = 0; (void)cudaGetLastError(); }
+        if (cudaOccupancyMaxActiveClusters(&nc, fused_pass_kernel<RPT, CBW, NST>, &cfg) != cudaSuccess) { nc = 0; (void)cudaGetLastError(); }
         g_max_clusters[ri][CS] = nc;
     }
 }
@@ -1016,12 +1023,14 @@ static void fused_set_attributes()
 {
     static DeviceOnce once;
     if (!first_on_device(once)) return;
-    SVD_CUDA_CHECK(cudaFuncSetAttribute(fused_pass_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FZ_SMEM_BYTES));
-    SVD_CUDA_CHECK(cudaFuncSetAttribute(fused_pass_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FZ_SMEM_BYTES));
-    SVD_CUDA_CHECK(cudaFuncSetAttribute(fused_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FZ_SMEM_BYTES));
-    query_clusters_t<2>(0);
-    query_clusters_t<4>(1);
-    query_clusters_t<8>(2);
+    SVD_CUDA_CHECK(cudaFuncSetAttribute(fused_pass_kernel<2, 4, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FZ_SMEM_BYTES));
+    SVD_CUDA_CHECK(cudaFuncSetAttribute(fused_pass_kernel<4, 2, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FZ_SMEM_BYTES));
+    SVD_CUDA_CHECK(cudaFuncSetAttribute(fused_pass_kernel<8, 1, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FZ_SMEM_BYTES));
+    SVD_CUDA_CHECK(cudaFuncSetAttribute(fused_pass_kernel<8, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FZ_SMEM_BYTES));
+    query_clusters_t<2, 4, 6>(0);
+    query_clusters_t<4, 2, 6>(1);
+    query_clusters_t<8, 1, 6>(2);
+    query_clusters_t<8, 2, 4>(3);
     if (getenv("SVD_GPU_VERBOSE")) {
         fprintf(stderr, "fused pass: co-resident clusters by size 1..%d (RPT 8):", FZ_MAXCS);
         for (int CS = 1; CS <= FZ_MAXCS; ++CS) fprintf(stderr, " %d", g_max_clusters[2][CS]);
@@ -1201,6 +1210,7 @@ void bidiag_device(int m, int n, double *A, long lda, double *alpha, double *bet
     const char *e1 = getenv("SVD_GPU_FUSED_MIN_ROWS"), *e2 = getenv("SVD_GPU_FUSED_MIN_COLS");
     const int fz_min_rows = e1 ? atoi(e1) : FZ_MIN_ROWS, fz_min_cols = e2 ? atoi(e2) : FZ_MIN_COLS;
     // SVD_GPU_TAIL=0/1: finish on chip once the trailing block fits into shared memory (bidiag_tail.cuh)
+    g_fz_wide = getenv("SVD_GPU_FZ_WIDE") ? atoi(getenv("SVD_GPU_FZ_WIDE")) != 0 : false;
     const int xw_mode = getenv("SVD_GPU_XW") ? atoi(getenv("SVD_GPU_XW")) : 1;     // finish_xw: 0 never, 1 long columns, 2 always
     // SVD_GPU_PPK=1: whole panels of single-CTA passes in one persistent cooperative launch (bidiag_panel.cuh)
     const bool use_ppk = use_fused && (getenv("SVD_GPU_PPK") ? atoi(getenv("SVD_GPU_PPK")) != 0 : PPK_DEFAULT_ON);
@@ -1255,6 +1265,7 @@ void bidiag_device(int m, int n, double *A, long lda, double *alpha, double *bet
         FusedPlan pl = {false, 1, 4, 0, 0, 0};
         if (use_fused && !tail && do_col && do_row) pl = plan_fused(i, m, n, mpad, nsm, fz_min_rows < 2 ? 2 : fz_min_rows, fz_min_cols < 1 ? 1 : fz_min_cols);
         // a whole panel at once: every step of it a regular single-CTA fused step with at least one tile per CTA
+        if (pl.ok && use_ppk && k == 0 && pl.CS == 1) pl = plan_fused(i, m, n, mpad, nsm, 2, 1, true);   // the panel kernel has the classic tiles
         if (pl.ok && use_ppk && k == 0 && pl.CS == 1 && nb <= 32 && g_panel_ctas > 0 && pl.NC <= g_panel_ctas &&
             i + nb < mn - 1 && i + nb < n - 2 && n - (i + nb) >= pl.NC * FZ_CBW_MAX && m - (i + nb) >= 64 &&
             ceil_div(Lb, 32) < pl.NC && (!hook || !hook->fn || hook->every <= 0 || hook->every % nb == 0)) {

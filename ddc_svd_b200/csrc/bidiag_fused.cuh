@@ -231,11 +231,15 @@ __device__ __forceinline__ void fz_col_axpy(const double *__restrict__ col, doub
 }
 
 #define FZ_TR(slot, nt) do { if (a.trace && blockIdx.x == 0 && (nt) < 256) a.trace[(nt) * 8 + (slot)] = clock64(); } while (0)
-// RPT = row pairs per sweep thread (rows per CTA <= 512*RPT <= 4096), CBW = 8/RPT columns per tile
-template <int RPT>
+// RPT = row pairs per sweep thread (rows per CTA <= 512*RPT <= 4096), CBW columns per tile, NST stages of
+// FZ_STAGES*FZ_STAGE/NST doubles.  Classic geometries: CBW = 8/RPT, 6 stages of 32 KB.  <8, 2, 4>: two columns of up
+// to 3072 rows per 48 KB stage - the per-tile role chain (barrier hops, lane reduction, reducer, finisher) is the
+// limit for short columns, and a tile of two columns pays it once for twice the data.
+template <int RPT, int CBW, int NST>
 __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedArgs a)
 {
-    constexpr int CBW = 8 / RPT;
+    constexpr int STG = FZ_STAGES * FZ_STAGE / NST;       // doubles per stage
+    static_assert(NST <= FZ_STAGES && CBW <= FZ_CBW_MAX && FZ_XR >= 2 * NST, "fused pass geometry");
     constexpr int WP = SVDGPU_FZ_WP ? FZ_CBW_MAX / CBW : 1;    // lane partials each sweep-1 warp leaves per column (fills the same 32 slots per stage)
     extern __shared__ __align__(128) unsigned char fz_smem[];
     double *tile = reinterpret_cast<double *>(fz_smem);
@@ -272,7 +276,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
     if (len < 0) len = 0;
 
     if (tid == 0) {
-        for (int s = 0; s < FZ_STAGES; ++s) {
+        for (int s = 0; s < NST; ++s) {
             fz_mbar_init(full + s, 2);          // TMA transaction arrive + helper
             fz_mbar_init(empty + s, FZ_GW + 1); // the sweep-2 warps + the finisher (it reads the stage's panel rows)
             fz_mbar_init(wbar + s, FZ_GW);      // the sweep-1 warps of the tile's group
@@ -287,7 +291,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
     const int ntiles = (a.T > g) ? (a.T - g + NC - 1) / NC : 0;
     int npre = 0;
     if (a.prefetch) {
-        npre = ntiles < FZ_STAGES ? ntiles : FZ_STAGES;
+        npre = ntiles < NST ? ntiles : NST;
         if (tid == 0) {
             for (int nt = 0; nt < npre; ++nt) {
                 const int j0 = i + 1 + (g + nt * NC) * CBW;
@@ -298,7 +302,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
                 if (bytes) {
                     fz_mbar_arrive_expect_tx(full + nt, bytes);
                     for (int q = 0; q < ncols; ++q)
-                        fz_bulk_g2s(tile + (size_t)nt * FZ_STAGE + (size_t)q * Lc, a.A + rs + (long)(j0 + q) * a.lda,
+                        fz_bulk_g2s(tile + (size_t)nt * STG + (size_t)q * Lc, a.A + rs + (long)(j0 + q) * a.lda,
                                     (unsigned)len * 8u, full + nt);
                 } else {
                     fz_mbar_arrive(full + nt);
@@ -405,8 +409,8 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
     if (warp == 0) {
         // ============================ TMA producer warp ============================
         for (int nt = npre; nt < ntiles; ++nt) {
-            const int s = nt % FZ_STAGES;
-            fz_mbar_wait(empty + s, ((nt / FZ_STAGES) & 1) ^ 1);
+            const int s = nt % NST;
+            fz_mbar_wait(empty + s, ((nt / NST) & 1) ^ 1);
             if (lane == 0) {
                 const int j0 = i + 1 + (g + nt * NC) * CBW;
                 int ncols = a.n - j0;
@@ -416,7 +420,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
                 if (bytes) {
                     fz_mbar_arrive_expect_tx(full + s, bytes);
                     for (int q = 0; q < ncols; ++q)
-                        fz_bulk_g2s(tile + (size_t)s * FZ_STAGE + (size_t)q * Lc, a.A + rs + (long)(j0 + q) * a.lda,
+                        fz_bulk_g2s(tile + (size_t)s * STG + (size_t)q * Lc, a.A + rs + (long)(j0 + q) * a.lda,
                                     (unsigned)len * 8u, full + s);
                 } else {
                     fz_mbar_arrive(full + s);
@@ -428,7 +432,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
         // per tile column j: a_ij, corr_j = Y[j,:].vTv + U[j,:].xTv, g_j = rowV.Y[j,:] + rowX.U[j,:]
         // and a copy of the panel rows for the dot partials; all loads are issued before any use
         for (int nt = warp - 1; nt < ntiles; nt += FZ_HW) {
-            const int s = nt % FZ_STAGES;
+            const int s = nt % NST;
             const int j0 = i + 1 + (g + nt * NC) * CBW;
             int ncols = a.n - j0;
             if (ncols > CBW) ncols = CBW;
@@ -445,7 +449,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
             } else {
                 helper_load(nt, yk, uk, aij);
             }
-            fz_mbar_wait(empty + s, ((nt / FZ_STAGES) & 1) ^ 1);     // stage (and its helper slots) free
+            fz_mbar_wait(empty + s, ((nt / NST) & 1) ^ 1);     // stage (and its helper slots) free
 #pragma unroll
             for (int q = 0; q < CBW; ++q) {
                 double corr = 0.0, gg = 0.0;
@@ -474,8 +478,8 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
         // ============================== reducer warp ==============================
         // combines the sweep-1 warps' column sums of a tile and ships them to every CTA of the cluster
         for (int nt = 0; nt < ntiles; ++nt) {
-            const int s = nt % FZ_STAGES, xs = nt % FZ_XR;
-            fz_mbar_wait(wbar + s, (nt / FZ_STAGES) & 1);
+            const int s = nt % NST, xs = nt % FZ_XR;
+            fz_mbar_wait(wbar + s, (nt / NST) & 1);
             if (lane == 0) FZ_TR(3, nt);
             double vals[CBW];
 #pragma unroll
@@ -512,7 +516,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
         double dY[2] = {0.0, 0.0}, dU[2] = {0.0, 0.0}, rr2 = 0.0, yr = 0.0;
         const int fin = warp - FZ_W_FIN;
         for (int pt = fin; pt < ntiles; pt += FZ_NFIN) {
-            const int s = pt % FZ_STAGES, xs = pt % FZ_XR;
+            const int s = pt % NST, xs = pt % FZ_XR;
             fz_mbar_wait(xbar + xs, (pt / FZ_XR) & 1);
             if (lane == 0) FZ_TR(4, pt);
             const int ncols = hn[s];
@@ -610,11 +614,11 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
             }
         }
         for (int nt = 0; nt < ntiles; ++nt) {
-            const int s = nt % FZ_STAGES;
-            fz_mbar_wait(full + s, (nt / FZ_STAGES) & 1);
+            const int s = nt % NST;
+            fz_mbar_wait(full + s, (nt / NST) & 1);
             if (wig == 0 && lane == 0) FZ_TR(1, nt);
             const int ncols = hn[s];
-            const double *tl = tile + (size_t)s * FZ_STAGE;
+            const double *tl = tile + (size_t)s * STG;
 #pragma unroll
             for (int q = 0; q < CBW; ++q) {
                 const double pq = (q < ncols) ? fz_col_dot<RPT>(tl + (size_t)q * Lc, creg, gt, len) : 0.0;
@@ -638,11 +642,11 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) fused_pass_kernel(const FusedAr
 #pragma unroll
         for (int u = 0; u < RPT; ++u) acc[u] = make_double2(0.0, 0.0);
         for (int nt = 0; nt < ntiles; ++nt) {
-            const int s = nt % FZ_STAGES;
-            fz_mbar_wait(rbar + s, (nt / FZ_STAGES) & 1);
+            const int s = nt % NST;
+            fz_mbar_wait(rbar + s, (nt / NST) & 1);
             if (wig == 0 && lane == 0) FZ_TR(6, nt);
             const int ncols = hn[s];
-            const double *tl = tile + (size_t)s * FZ_STAGE;
+            const double *tl = tile + (size_t)s * STG;
 #pragma unroll
             for (int q = 0; q < CBW; ++q) {
                 if (q < ncols) fz_col_axpy<RPT>(tl + (size_t)q * Lc, rq[s * FZ_CBW_MAX + q], acc, gt, len);
