@@ -43,9 +43,9 @@ sys.path.insert(0, ROOT)
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE captured launch of the dominant kernel
 # (ncu --set full, round 2 capture, profiles/r02_ncu_summary.md): fused_pass_kernel at step i=1500 of n=16384
 # (algorithmic single-read bytes of that launch: 8*(16384-1500)*(16384-1501) = 1.772e9) and at step 1000 of n=4096
-NCU_TRAFFIC = {16384: 1.780506e9 + 4.453888e6, 4096: 77.3888e6 + 1.939456e6}
+NCU_TRAFFIC = {16384: 1.780513e9 + 4.743680e6, 4096: 77.3888e6 + 1.939456e6}
 NCU_TRAFFIC_NOTE = ("dram__bytes_read.sum + dram__bytes_write.sum of ONE fused_pass_kernel launch (ncu --set full): "
-                    "n=16384 step 1500 (single-read algorithmic bytes of that launch 1.772e9, 280.4 us), "
+                    "n=16384 step 1500 (single-read algorithmic bytes of that launch 1.772e9, 263.3 us), "
                     "n=4096 step 1000 (76.7e6, 23.8 us); profiles/r02_ncu_summary.md")
 METRIC = "svd_gpu seconds"
 UNIT = "s"
